@@ -1,0 +1,198 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle.cpp header).  May be
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs; never by prestige_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class WcsphParams(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("pad", C.c_int32), ("kfac", C.c_double), ("rho0", C.c_double),
+                ("c0", C.c_double), ("gamma", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
+                ("g", C.c_double * 3)]
+
+
+class DemParams(C.Structure):
+    _fields_ = [("model", C.c_int32), ("K", C.c_int32), ("kn", C.c_double), ("gn", C.c_double),
+                ("kt", C.c_double), ("gt", C.c_double), ("mu", C.c_double), ("dt", C.c_double),
+                ("Estar", C.c_double), ("Gstar", C.c_double), ("erest", C.c_double)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n", C.c_int32 * 3), ("lo", C.c_double * 3), ("cell", C.c_double)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_num_threads.restype = C.c_int
+        for sfx in ("f64", "f32"):
+            getattr(_LIB, f"orc_pairs_allpairs_{sfx}").restype = C.c_int64
+            getattr(_LIB, f"orc_pairs_cells_{sfx}").restype = C.c_int64
+            getattr(_LIB, f"orc_dem_forces_{sfx}").restype = C.c_int
+    return _LIB
+
+
+def _sfx(a: np.ndarray) -> str:
+    return {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32"}[a.dtype]
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
+def make_grid(dim, lo, hi, cell) -> Grid:
+    import math
+    g = Grid()
+    g.dim = dim
+    for a in range(3):
+        g.n[a] = max(1, int(math.ceil((hi[a] - lo[a]) / cell))) if a < dim else 1
+        g.lo[a] = lo[a]
+    g.cell = cell
+    return g
+
+
+def wcsph_params(dim: int, P: dict) -> WcsphParams:
+    w = WcsphParams()
+    w.dim = dim
+    w.kfac = P.get("kfac", 2.0)
+    w.rho0, w.c0, w.gamma, w.alpha, w.beta = P["rho0"], P["c0"], P["gamma"], P["alpha"], P["beta"]
+    w.g[0], w.g[1], w.g[2] = P.get("gx", 0.0), P.get("gy", 0.0), P.get("gz", 0.0)
+    return w
+
+
+def dem_params(P: dict, K: int) -> DemParams:
+    d = DemParams()
+    d.model = int(P.get("dem_model", 0))
+    d.K = K
+    d.kn, d.gn, d.kt, d.gt, d.mu, d.dt = P["kn"], P["gn"], P["kt"], P["gt"], P["mu"], P["dt"]
+    d.Estar, d.Gstar, d.erest = P.get("Estar", 0.0), P.get("Gstar", 0.0), P.get("erest", 1.0)
+    return d
+
+
+def eq1_allpairs(mass: np.ndarray, force: np.ndarray) -> np.ndarray:
+    """force[i] += sum_j mass[j], the loop simple_cpu.rs:7-16 emits for lib.rs:10."""
+    force = np.ascontiguousarray(force.copy())
+    getattr(lib(), f"orc_eq1_allpairs_{_sfx(mass)}")(C.c_int64(len(mass)), _p(np.ascontiguousarray(mass)), _p(force))
+    return force
+
+
+def _zeros_like_opt(a, dim):
+    return a if a is not None else None
+
+
+def pairs(dim, x, y, z, s, mode=0, kfac=2.0, grid: Grid | None = None, cap=None):
+    """Neighbour (mode 0, s = h) or contact (mode 1, s = radius) set as an (n_pairs, 2) uint32 array
+    sorted lexicographically.  grid=None -> all-pairs (truth); else cell list.  Also returns the
+    minimum relative distance of any pair from the cutoff (all-pairs mode only)."""
+    n = len(x)
+    z = z if z is not None else np.zeros_like(x)
+    cap = cap or max(1024, 128 * n)
+    oi = np.empty(cap, np.uint32); oj = np.empty(cap, np.uint32)
+    sfx = _sfx(x)
+    margin = C.c_double(0.0)
+    if grid is None:
+        cnt = getattr(lib(), f"orc_pairs_allpairs_{sfx}")(C.c_int(dim), C.c_int(mode), C.c_double(kfac), C.c_int64(n),
+                                                          _p(x), _p(y), _p(z), _p(s), _p(oi), _p(oj), C.c_int64(cap),
+                                                          C.byref(margin))
+    else:
+        cnt = getattr(lib(), f"orc_pairs_cells_{sfx}")(C.byref(grid), C.c_int(mode), C.c_double(kfac), C.c_int64(n),
+                                                       _p(x), _p(y), _p(z), _p(s), _p(oi), _p(oj), C.c_int64(cap))
+    assert cnt <= cap, "pair buffer too small"
+    pr = np.stack([oi[:cnt], oj[:cnt]], axis=1)
+    pr = pr[np.lexsort((pr[:, 1], pr[:, 0]))]
+    return pr, margin.value
+
+
+def wcsph(dim, P: dict, a: dict, grid: Grid | None = None, sorted_step: bool = False):
+    """EOS + continuity + momentum.  Returns dict p, au, av, aw, arho in the input order."""
+    x = np.ascontiguousarray(a["x"]); n = len(x); dt = x.dtype
+    z = np.ascontiguousarray(a["z"]) if dim == 3 else np.zeros_like(x)
+    w = np.ascontiguousarray(a["w"]) if dim == 3 else np.zeros_like(x)
+    out = {k: np.zeros(n, dt) for k in ("p", "au", "av", "aw", "arho")}
+    args = [_p(x), _p(np.ascontiguousarray(a["y"])), _p(z), _p(np.ascontiguousarray(a["u"])),
+            _p(np.ascontiguousarray(a["v"])), _p(w), _p(np.ascontiguousarray(a["rho"])),
+            _p(np.ascontiguousarray(a["m"])), _p(np.ascontiguousarray(a["h"])),
+            _p(out["p"]), _p(out["au"]), _p(out["av"]), _p(out["aw"]), _p(out["arho"])]
+    wp = wcsph_params(dim, P)
+    sfx = _sfx(x)
+    if grid is None:
+        getattr(lib(), f"orc_wcsph_allpairs_{sfx}")(C.byref(wp), C.c_int64(n), *args)
+    elif sorted_step:
+        getattr(lib(), f"orc_wcsph_step_sorted_{sfx}")(C.byref(wp), C.byref(grid), C.c_int64(n), *args)
+    else:
+        getattr(lib(), f"orc_wcsph_cells_{sfx}")(C.byref(wp), C.byref(grid), C.c_int64(n), *args)
+    return out
+
+
+def eos(dim, P: dict, rho: np.ndarray) -> np.ndarray:
+    p = np.zeros_like(rho)
+    wp = wcsph_params(dim, P)
+    getattr(lib(), f"orc_wcsph_eos_{_sfx(rho)}")(C.byref(wp), C.c_int64(len(rho)), _p(np.ascontiguousarray(rho)), _p(p))
+    return p
+
+
+def empty_history(n: int, K: int, dt=np.float64):
+    return {"hist_n": np.zeros(n, np.int32), "hist_id": np.zeros((K, n), np.uint32),
+            "hist_x": np.zeros((K, n), dt), "hist_y": np.zeros((K, n), dt), "hist_z": np.zeros((K, n), dt)}
+
+
+def dem(P: dict, K: int, a: dict, hist: dict | None = None, ids: np.ndarray | None = None, grid: Grid | None = None):
+    """One DEM force evaluation.  Returns (forces dict, new history dict, overflow flag)."""
+    x = np.ascontiguousarray(a["x"]); n = len(x); dt = x.dtype
+    hist = hist or empty_history(n, K, dt)
+    ids = np.arange(n, dtype=np.uint32) if ids is None else np.ascontiguousarray(ids, np.uint32)
+    new = empty_history(n, K, dt)
+    out = {k: np.zeros(n, dt) for k in ("fx", "fy", "fz", "tx", "ty", "tz")}
+    dp = dem_params(P, K)
+    c = lambda k: _p(np.ascontiguousarray(a[k]))
+    ov = getattr(lib(), f"orc_dem_forces_{_sfx(x)}")(
+        C.byref(dp), C.byref(grid) if grid is not None else None, C.c_int64(n),
+        _p(x), c("y"), c("z"), c("u"), c("v"), c("w"), c("wx"), c("wy"), c("wz"), c("rad"), c("m"), _p(ids),
+        _p(np.ascontiguousarray(hist["hist_n"])), _p(np.ascontiguousarray(hist["hist_id"])),
+        _p(np.ascontiguousarray(hist["hist_x"])), _p(np.ascontiguousarray(hist["hist_y"])),
+        _p(np.ascontiguousarray(hist["hist_z"])),
+        _p(new["hist_n"]), _p(new["hist_id"]), _p(new["hist_x"]), _p(new["hist_y"]), _p(new["hist_z"]),
+        _p(out["fx"]), _p(out["fy"]), _p(out["fz"]), _p(out["tx"]), _p(out["ty"]), _p(out["tz"]))
+    return out, new, int(ov)
+
+
+def history_as_dict(hist: dict, ids: np.ndarray | None = None) -> dict:
+    """{(id_i, id_j): (xi_x, xi_y, xi_z)} -- history compared as a keyed set, slot order is free."""
+    n = len(hist["hist_n"])
+    ids = np.arange(n) if ids is None else ids
+    d = {}
+    for i in np.nonzero(hist["hist_n"])[0]:
+        for k in range(hist["hist_n"][i]):
+            d[(int(ids[i]), int(hist["hist_id"][k, i]))] = (hist["hist_x"][k, i], hist["hist_y"][k, i], hist["hist_z"][k, i])
+    return d
