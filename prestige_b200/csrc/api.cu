@@ -1,0 +1,412 @@
+// api.cu -- the extern "C" surface declared in include/prestige_b200.h.
+// Context, named arrays, parameters, transfers, equation-set dispatch (the reference's fuse() made
+// real: prestige/src/equations/fuse.rs:14-40 -> one fused kernel), and the step loop.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <set>
+
+#include "pst_internal.h"
+
+static thread_local std::string g_create_err;
+
+pst_status pst_fail(const pst_ctx* ctx, pst_status s, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return s;
+}
+
+PstArray* pst_find(pst_ctx* ctx, const char* name) {
+    auto it = ctx->index.find(name);
+    return it == ctx->index.end() ? nullptr : &ctx->arrays[it->second];
+}
+double pst_param(pst_ctx* ctx, const char* name, double dflt) {
+    auto it = ctx->params.find(name);
+    return it == ctx->params.end() ? dflt : it->second;
+}
+int pst_option(pst_ctx* ctx, const char* name, int dflt) {
+    auto it = ctx->options.find(name);
+    return it == ctx->options.end() ? dflt : it->second;
+}
+
+static size_t dtype_size(int dt) { return (dt == PST_F64) ? 8 : 4; }
+
+static pst_status array_create(pst_ctx* ctx, const char* name, int dtype, uint32_t flags, int rows) {
+    if (!name || !*name) return pst_fail(ctx, PST_EINVAL, "array name is empty");
+    if (pst_find(ctx, name)) return pst_fail(ctx, PST_EINVAL, "array '%s' already exists", name);
+    if (dtype == PST_REAL) dtype = ctx->f64 ? PST_F64 : PST_F32;
+    if (dtype < PST_F32 || dtype > PST_I32) return pst_fail(ctx, PST_EINVAL, "array '%s': bad dtype %d", name, dtype);
+    PstArray a;
+    a.name = name; a.dtype = dtype; a.flags = flags; a.rows = rows; a.esize = dtype_size(dtype);
+    const size_t bytes = (size_t)rows * (ctx->capacity + 2 * ctx->ghost_cap) * a.esize;
+    const int nbuf = (flags & PST_ARRAY_PERSISTENT) ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) {
+        cudaError_t e = cudaMalloc((void**)&a.buf[b], bytes);
+        if (e != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "cudaMalloc(%zu) for '%s': %s", bytes, name, cudaGetErrorString(e));
+        PST_CUDA(ctx, cudaMemsetAsync(a.buf[b], 0, bytes, ctx->stream));
+    }
+    if (nbuf == 1) a.buf[1] = nullptr;
+    ctx->index[name] = (int)ctx->arrays.size();
+    ctx->arrays.push_back(a);
+    return PST_OK;
+}
+
+extern "C" {
+
+const char* pst_version(void) { return "prestige_b200 0.1 (sm_100a)"; }
+
+const char* pst_last_error(const pst_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
+    if (!cfg || !out) return pst_fail(nullptr, PST_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(pst_config))
+        return pst_fail(nullptr, PST_EINVAL, "pst_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(pst_config));
+    if (cfg->dim != 2 && cfg->dim != 3) return pst_fail(nullptr, PST_EINVAL, "dim must be 2 or 3");
+    if (cfg->real != PST_F32 && cfg->real != PST_F64) return pst_fail(nullptr, PST_EINVAL, "real must be PST_F32 or PST_F64");
+    if (cfg->key != PST_KEY_LINEAR && cfg->key != PST_KEY_MORTON) return pst_fail(nullptr, PST_EINVAL, "bad key mode");
+    if (!(cfg->cell_size > 0)) return pst_fail(nullptr, PST_EINVAL, "cell_size must be > 0");
+    if (cfg->capacity == 0 || cfg->capacity + 2 * cfg->ghost_capacity >= (1ull << 31))
+        return pst_fail(nullptr, PST_EINVAL, "capacity must be in [1, 2^31)");
+    if ((cfg->physics & PST_PHYS_DEM) && cfg->dim != 3) return pst_fail(nullptr, PST_EINVAL, "DEM needs dim = 3");
+    if (cfg->max_contacts < 0 || cfg->max_contacts > 32) return pst_fail(nullptr, PST_EINVAL, "max_contacts must be in [0, 32]");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return pst_fail(nullptr, PST_ECUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return pst_fail(nullptr, PST_EINVAL, "device %d out of range", cfg->device);
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return pst_fail(nullptr, PST_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    pst_ctx* ctx = new pst_ctx();
+    ctx->cfg = *cfg;
+    ctx->f64 = cfg->real == PST_F64;
+    ctx->dim = cfg->dim;
+    ctx->capacity = cfg->capacity;
+    ctx->ghost_cap = cfg->ghost_capacity;
+    auto bail = [&](pst_status s) { g_create_err = ctx->err; pst_destroy(ctx); return s; };
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        pst_fail(ctx, PST_ECUDA, "cudaStreamCreate failed");
+        return bail(PST_ECUDA);
+    }
+    // grid
+    PstGrid& g = ctx->grid;
+    g.dim = cfg->dim;
+    g.cell = cfg->cell_size;
+    g.inv_cell = 1.0 / cfg->cell_size;
+    g.morton = cfg->key == PST_KEY_MORTON;
+    double ncell_total = 1;
+    int nmax = 1;
+    for (int a = 0; a < 3; ++a) {
+        g.lo[a] = cfg->lo[a];
+        g.n[a] = 1;
+        if (a < cfg->dim) {
+            const double ext = cfg->hi[a] - cfg->lo[a];
+            if (!(ext >= 0)) { pst_fail(ctx, PST_EINVAL, "hi[%d] < lo[%d]", a, a); return bail(PST_EINVAL); }
+            g.n[a] = std::max(1, (int)std::ceil(ext / cfg->cell_size));
+        }
+        ncell_total *= g.n[a];
+        nmax = std::max(nmax, g.n[a]);
+    }
+    g.cx_lo = 0; g.cx_hi = g.n[0] - 1;
+    if (g.morton) {
+        g.bits = 1;
+        while ((1 << g.bits) < nmax) ++g.bits;
+        if (g.bits > (cfg->dim == 3 ? 10 : 15)) { pst_fail(ctx, PST_EINVAL, "grid too large for Morton keys"); return bail(PST_EINVAL); }
+        g.key_bits = g.bits * cfg->dim;
+        g.ncells = 1u << g.key_bits;
+    } else {
+        if (ncell_total >= 2147483647.0) { pst_fail(ctx, PST_EINVAL, "grid has too many cells (%g)", ncell_total); return bail(PST_EINVAL); }
+        g.ncells = (uint32_t)ncell_total;
+        g.key_bits = 1;
+        while ((1ull << g.key_bits) < g.ncells) ++g.key_bits;
+    }
+    // default parameters
+    ctx->params = {{"rho0", 1000.0}, {"c0", 10.0}, {"gamma", 7.0}, {"alpha", 0.1}, {"beta", 0.0}, {"kfac", 2.0},
+                   {"gx", 0.0}, {"gy", 0.0}, {"gz", 0.0}, {"dem_model", 0.0}, {"kn", 1e5}, {"gn", 0.0}, {"kt", 2e4},
+                   {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}};
+    pst_status s = PST_OK;
+    auto mk = [&](const char* name, int dt, uint32_t fl, int rows = 1) { if (s == PST_OK) s = array_create(ctx, name, dt, fl, rows); };
+    const uint32_t P = PST_ARRAY_PERSISTENT, O = PST_ARRAY_OUTPUT;
+    mk("id", PST_U32, P);
+    if (cfg->physics & (PST_PHYS_WCSPH | PST_PHYS_DEM)) {
+        mk("x", PST_REAL, P); mk("y", PST_REAL, P); if (cfg->dim == 3) mk("z", PST_REAL, P);
+        mk("u", PST_REAL, P); mk("v", PST_REAL, P); if (cfg->dim == 3) mk("w", PST_REAL, P);
+        mk("m", PST_REAL, P); mk("tag", PST_I32, P);
+    }
+    if (cfg->physics & PST_PHYS_WCSPH) {
+        mk("rho", PST_REAL, P); mk("h", PST_REAL, P);
+        mk("p", PST_REAL, O); mk("por2", PST_REAL, O);
+        mk("au", PST_REAL, O); mk("av", PST_REAL, O); if (cfg->dim == 3) mk("aw", PST_REAL, O);
+        mk("arho", PST_REAL, O);
+    }
+    if (cfg->physics & PST_PHYS_DEM) {
+        mk("wx", PST_REAL, P); mk("wy", PST_REAL, P); mk("wz", PST_REAL, P);
+        mk("rad", PST_REAL, P); mk("inertia", PST_REAL, P);
+        mk("fx", PST_REAL, O); mk("fy", PST_REAL, O); mk("fz", PST_REAL, O);
+        mk("tx", PST_REAL, O); mk("ty", PST_REAL, O); mk("tz", PST_REAL, O);
+        if (cfg->max_contacts > 0) {
+            const int K = cfg->max_contacts;
+            mk("hist_n", PST_I32, P);
+            mk("hist_id", PST_U32, P, K);
+            mk("hist_x", PST_REAL, P, K); mk("hist_y", PST_REAL, P, K); mk("hist_z", PST_REAL, P, K);
+        }
+    }
+    if (s == PST_OK) s = pst_nnps_alloc(ctx);
+    if (s != PST_OK) return bail(s);
+    *out = ctx;
+    return PST_OK;
+}
+
+void pst_destroy(pst_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pst_comm_destroy(ctx);
+    for (auto& a : ctx->arrays) { cudaFree(a.buf[0]); if (a.buf[1]) cudaFree(a.buf[1]); }
+    cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
+    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->stage); cudaFree(ctx->d_flags);
+    cudaFree(ctx->d_counters);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+void* pst_stream(pst_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// Fetch device flags; turn a recorded contact overflow into PST_EOVERFLOW (never silent truncation).
+static pst_status check_flags(pst_ctx* ctx) {
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[0]) {
+        const int worst = ctx->h_flags[1];
+        PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
+        return pst_fail(ctx, PST_EOVERFLOW, "a particle has %d contacts > max_contacts = %d", worst, ctx->cfg.max_contacts);
+    }
+    return PST_OK;
+}
+
+pst_status pst_sync(pst_ctx* ctx) {
+    if (!ctx) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return check_flags(ctx);
+}
+
+pst_status pst_set_param(pst_ctx* ctx, const char* name, double value) {
+    if (!ctx || !name) return PST_EINVAL;
+    if (!ctx->params.count(name)) return pst_fail(ctx, PST_EINVAL, "unknown parameter '%s'", name);
+    ctx->params[name] = value;
+    ctx->eos_valid = false;
+    return PST_OK;
+}
+pst_status pst_get_param(pst_ctx* ctx, const char* name, double* value) {
+    if (!ctx || !name || !value) return PST_EINVAL;
+    auto it = ctx->params.find(name);
+    if (it == ctx->params.end()) return pst_fail(ctx, PST_EINVAL, "unknown parameter '%s'", name);
+    *value = it->second;
+    return PST_OK;
+}
+pst_status pst_set_option(pst_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return PST_EINVAL;
+    ctx->options[name] = value;
+    return PST_OK;
+}
+
+pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
+    if (!ctx) return PST_EINVAL;
+    if (n > ctx->capacity) return pst_fail(ctx, PST_ENOMEM, "count %llu > capacity %llu", (unsigned long long)n, (unsigned long long)ctx->capacity);
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    ctx->n = n;
+    ctx->n_ghost_l = ctx->n_ghost_r = 0;
+    ctx->ordered = false;
+    ctx->nbrs_valid = false;
+    ctx->eos_valid = false;
+    PST_TRY(pst_iota_ids(ctx));
+    if (PstArray* hn = pst_find(ctx, "hist_n")) {
+        const size_t stride = ctx->capacity + 2 * ctx->ghost_cap;
+        for (int b = 0; b < 2; ++b) PST_CUDA(ctx, cudaMemsetAsync(hn->buf[b], 0, stride * hn->esize, ctx->stream));
+    }
+    return PST_OK;
+}
+pst_status pst_get_count(pst_ctx* ctx, uint64_t* n_owned, uint64_t* n_ghost) {
+    if (!ctx) return PST_EINVAL;
+    if (n_owned) *n_owned = ctx->n;
+    if (n_ghost) *n_ghost = (uint64_t)(ctx->n_ghost_l + ctx->n_ghost_r);
+    return PST_OK;
+}
+
+pst_status pst_array_create(pst_ctx* ctx, const char* name, int dtype, uint32_t flags) {
+    if (!ctx) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return array_create(ctx, name, dtype, flags, 1);
+}
+
+pst_status pst_array(pst_ctx* ctx, const char* name, void** dev_ptr, size_t* n, int* dtype, int* rows) {
+    if (!ctx || !name) return PST_EINVAL;
+    PstArray* a = pst_find(ctx, name);
+    if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
+    if (dev_ptr) *dev_ptr = pst_ptr<char>(ctx, a);
+    if (n) *n = ctx->n;
+    if (dtype) *dtype = a->dtype;
+    if (rows) *rows = a->rows;
+    return PST_OK;
+}
+
+pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n) {
+    if (!ctx || !name || !host) return PST_EINVAL;
+    PstArray* a = pst_find(ctx, name);
+    if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
+    if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles (pst_set_count first)", name, n, (unsigned long long)ctx->n);
+    if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (int r = 0; r < a->rows; ++r) {
+        const char* src = (const char*)host + (size_t)r * n * a->esize;
+        if (!ctx->ordered) {
+            PST_CUDA(ctx, cudaMemcpyAsync(pst_ptr<char>(ctx, a, r), src, n * a->esize, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            PST_CUDA(ctx, cudaMemcpyAsync(ctx->stage, src, n * a->esize, cudaMemcpyHostToDevice, ctx->stream));
+            PST_TRY(pst_reorder_upload(ctx, a, r, n));
+        }
+    }
+    if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
+    if (a->name == "rho") ctx->eos_valid = false;
+    return PST_OK;
+}
+
+pst_status pst_download(pst_ctx* ctx, const char* name, void* host, size_t n) {
+    if (!ctx || !name || !host) return PST_EINVAL;
+    PstArray* a = pst_find(ctx, name);
+    if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
+    if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "download '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (int r = 0; r < a->rows; ++r) {
+        char* dst = (char*)host + (size_t)r * n * a->esize;
+        if (!ctx->ordered || a->name == "id") {
+            PST_CUDA(ctx, cudaMemcpyAsync(dst, pst_ptr<char>(ctx, a, r), n * a->esize, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            PST_TRY(pst_reorder_download(ctx, a, r, n));
+            PST_CUDA(ctx, cudaMemcpyAsync(dst, ctx->stage, n * a->esize, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    return check_flags(ctx);
+}
+
+void* pst_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void pst_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+pst_status pst_build_neighbours(pst_ctx* ctx) {
+    if (!ctx) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return pst_nnps_build(ctx);
+}
+
+pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
+    if (!ctx || !eq_names || n_eq <= 0) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    std::set<std::string> eqs;
+    for (int k = 0; k < n_eq; ++k) {
+        if (!eq_names[k]) return PST_EINVAL;
+        eqs.insert(eq_names[k]);
+    }
+    static const std::set<std::string> known = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact"};
+    for (auto& e : eqs)
+        if (!known.count(e)) return pst_fail(ctx, PST_EINVAL, "no hand-written kernel for equation '%s'", e.c_str());
+    // fuse(): group the set into the fused kernels that exist.  Bodies that share an i,j loop
+    // (continuity + momentum) run in ONE pair kernel; tait_eos is per-particle and runs first
+    // because momentum reads p[j].
+    if (eqs.count("eq1")) {
+        if (eqs.size() != 1) return pst_fail(ctx, PST_EINVAL, "eq1 cannot be fused with cutoff equations (it is an all-pairs loop)");
+        return pst_eq1_apply(ctx);
+    }
+    const bool wc = eqs.count("tait_eos") || eqs.count("continuity") || eqs.count("momentum");
+    if (wc && !(ctx->cfg.physics & PST_PHYS_WCSPH)) return pst_fail(ctx, PST_ESTATE, "context was created without PST_PHYS_WCSPH");
+    if (eqs.count("dem_contact") && !(ctx->cfg.physics & PST_PHYS_DEM)) return pst_fail(ctx, PST_ESTATE, "context was created without PST_PHYS_DEM");
+    if (eqs.count("tait_eos")) PST_TRY(pst_wcsph_eos(ctx));
+    if (eqs.count("continuity") || eqs.count("momentum")) {
+        if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pair equations");
+        if (eqs.count("momentum") && !ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "momentum reads p: apply tait_eos first (or in the same set)");
+        PST_TRY(pst_wcsph_forces(ctx, eqs.count("continuity") > 0, eqs.count("momentum") > 0));
+    }
+    if (eqs.count("dem_contact")) {
+        if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pair equations");
+        PST_TRY(pst_dem_forces(ctx));
+    }
+    return PST_OK;
+}
+
+pst_status pst_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size_t cap, size_t* n_pairs) {
+    if (!ctx || !n_pairs || (cap && (!i || !j))) return PST_EINVAL;
+    if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pst_dump_pairs");
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return pst_nnps_dump_pairs(ctx, mode, i, j, cap, n_pairs);
+}
+
+pst_status pst_integrate(pst_ctx* ctx, double dt) {
+    if (!ctx) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (ctx->cfg.physics & PST_PHYS_WCSPH) PST_TRY(pst_wcsph_integrate(ctx, dt));
+    if (ctx->cfg.physics & PST_PHYS_DEM) PST_TRY(pst_dem_integrate(ctx, dt));
+    ctx->nbrs_valid = false;
+    ctx->eos_valid = false;
+    return PST_OK;
+}
+
+pst_status pst_step(pst_ctx* ctx, double dt, int n_steps) {
+    if (!ctx || n_steps < 0) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (int k = 0; k < n_steps; ++k) {
+        PST_TRY(pst_nnps_build(ctx));
+        if (ctx->comm) PST_TRY(pst_halo_exchange(ctx));
+        if (ctx->cfg.physics & PST_PHYS_WCSPH) {
+            PST_TRY(pst_wcsph_eos(ctx));
+            PST_TRY(pst_wcsph_forces(ctx, true, true));
+        }
+        if (ctx->cfg.physics & PST_PHYS_DEM) {
+            ctx->params["dt"] = dt;
+            PST_TRY(pst_dem_forces(ctx));
+        }
+        PST_TRY(pst_integrate(ctx, dt));
+    }
+    return PST_OK;
+}
+
+pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value) {
+    if (!ctx || !name || !value) return PST_EINVAL;
+    const std::string s = name;
+    if (s == "launches") { *value = (double)ctx->launches; return PST_OK; }
+    if (s == "n_cells") { *value = (double)ctx->grid.ncells; return PST_OK; }
+    if (s == "key_bits") { *value = (double)ctx->grid.key_bits; return PST_OK; }
+    if (s == "nx") { *value = ctx->grid.n[0]; return PST_OK; }
+    if (s == "ny") { *value = ctx->grid.n[1]; return PST_OK; }
+    if (s == "nz") { *value = ctx->grid.n[2]; return PST_OK; }
+    if (s == "n_ghost_l") { *value = (double)ctx->n_ghost_l; return PST_OK; }
+    if (s == "n_ghost_r") { *value = (double)ctx->n_ghost_r; return PST_OK; }
+    if (s == "ordered") { *value = ctx->ordered; return PST_OK; }
+    if (s == "contacts_total") {  // sum of hist_n over owned particles
+        PstArray* hn = pst_find(ctx, "hist_n");
+        if (!hn) return pst_fail(ctx, PST_EINVAL, "no contact history in this context");
+        std::vector<int32_t> h(ctx->n);
+        PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+        PST_CUDA(ctx, cudaMemcpyAsync(h.data(), pst_ptr<int32_t>(ctx, hn), ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        double t = 0;
+        for (auto v : h) t += v;
+        *value = t;
+        return PST_OK;
+    }
+    return pst_fail(ctx, PST_EINVAL, "unknown stat '%s'", name);
+}
+
+}  // extern "C"

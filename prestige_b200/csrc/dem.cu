@@ -1,0 +1,200 @@
+// dem.cu -- discrete-element contact forces with per-pair tangential history.
+// Linear spring-dashpot or Hertz-Mindlin normal/tangential law, Coulomb cap, torque; history rows
+// keyed by the partner's STABLE id so they survive every re-sort.
+// No reference code exists for this physics; the loop shape it honours is the reference's gather
+// (prestige/src/codegen/simple_cpu.rs:7-16: write only [i]); each side of a contact evaluates its
+// own copy, and the operand order below makes F_ji = -F_ij and xi_ji = -xi_ij bit-exact.
+//
+// One thread per particle.  Cells hold ~1 sphere, so the 27-cell stencil is 9 short contiguous runs
+// (28 candidates, ~6 contacts): the kernel is a latency/bandwidth-bound gather, not FP64-bound.
+// History is slot-major ([k][particle]) so slot k of neighbouring threads coalesces; the pass reads
+// the current buffer (already permuted by k_remap_history) and writes the other one, then flips.
+#include "pst_internal.h"
+
+namespace {
+
+constexpr int kThreads = 128;
+inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <class R>
+struct DemConst {
+    int model, K;
+    R kn, gn, kt, gt, mu, dt, Estar, Gstar, damp_c;  // damp_c = -2 sqrt(5/6) beta_e  (> 0)
+};
+
+template <class R>
+struct DemArgs {
+    const R *x, *y, *z, *u, *v, *w, *wx, *wy, *wz, *rad, *m;
+    const uint32_t* id;
+    const int32_t* hn_in; const uint32_t* hid_in; const R *hx_in, *hy_in, *hz_in;
+    int32_t* hn_out; uint32_t* hid_out; R *hx_out, *hy_out, *hz_out;
+    R *fx, *fy, *fz, *tx, *ty, *tz;
+    const int32_t* cell_start;
+    int32_t* flags;
+    size_t stride;
+    int n;
+};
+
+template <class R, bool MORTON>
+__global__ void __launch_bounds__(kThreads) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n) return;
+    const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
+    const R ui = A.u[s], vi = A.v[s], wi = A.w[s];
+    const R ri = A.rad[s], mi = A.m[s];
+    const R owx = mul_rn(ri, A.wx[s]), owy = mul_rn(ri, A.wy[s]), owz = mul_rn(ri, A.wz[s]);   // R_i w_i
+    const int nold = A.hn_in[s];
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1);
+    R fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    int cnt = 0;
+    for_each_run<3, MORTON>(g, A.cell_start, cx, cy, cz, [&](int b, int e) {
+        for (int j = b; j < e; ++j) {
+            const R dx = xi - A.x[j], dy = yi - A.y[j], dz = zi - A.z[j];
+            const R r2 = dist2<3, R>(dx, dy, dz);
+            const R rj = A.rad[j];
+            const R rs = add_rn(ri, rj);
+            if (!(r2 < mul_rn(rs, rs)) || !(r2 > (R)0) || j == s) continue;
+            const R r = sqrt(r2);
+            const R rinv = (R)1 / r;
+            const R nx = dx * rinv, ny = dy * rinv, nz = dz * rinv;
+            const R delta = rs - r;
+            // R_i w_i + R_j w_j as a commutative sum of two rounded products (no FMA), so both sides of the
+            // contact see the same bits and F_ji = -F_ij exactly
+            const R ox = add_rn(owx, mul_rn(rj, A.wx[j])), oy = add_rn(owy, mul_rn(rj, A.wy[j])), oz = add_rn(owz, mul_rn(rj, A.wz[j]));
+            const R vcx = (ui - A.u[j]) - (oy * nz - oz * ny);
+            const R vcy = (vi - A.v[j]) - (oz * nx - ox * nz);
+            const R vcz = (wi - A.w[j]) - (ox * ny - oy * nx);
+            const R vn = vcx * nx + vcy * ny + vcz * nz;
+            const R vtx = vcx - vn * nx, vty = vcy - vn * ny, vtz = vcz - vn * nz;
+            R kn = C.kn, gn = C.gn, kt = C.kt, gt = C.gt;
+            if (C.model == 1) {
+                const R mj = A.m[j];
+                const R Rs = ri * rj / rs;
+                const R ms = mi * mj / (mi + mj);
+                const R sq = sqrt(Rs * delta);
+                const R Sn = (R)2 * C.Estar * sq, St = (R)8 * C.Gstar * sq;
+                kn = (R)(4.0 / 3.0) * C.Estar * sq;
+                kt = St;
+                gn = C.damp_c * sqrt(Sn * ms);
+                gt = C.damp_c * sqrt(St * ms);
+            }
+            const R fnm = kn * delta - gn * vn;
+            // history lookup by stable partner id (new contact => xi = 0)
+            const uint32_t pid = A.id[j];
+            R hx = 0, hy = 0, hz = 0;
+            for (int k = 0; k < nold; ++k) {
+                const size_t o = (size_t)k * A.stride + s;
+                if (A.hid_in[o] == pid) { hx = A.hx_in[o]; hy = A.hy_in[o]; hz = A.hz_in[o]; break; }
+            }
+            const R xn = hx * nx + hy * ny + hz * nz;
+            hx = hx - xn * nx + vtx * C.dt;
+            hy = hy - xn * ny + vty * C.dt;
+            hz = hz - xn * nz + vtz * C.dt;
+            R ftx = -kt * hx - gt * vtx, fty = -kt * hy - gt * vty, ftz = -kt * hz - gt * vtz;
+            const R ftm = sqrt(ftx * ftx + fty * fty + ftz * ftz);
+            const R fmax = C.mu * fabs(fnm);
+            if (ftm > fmax) {
+                const R sc = fmax / ftm;
+                ftx *= sc; fty *= sc; ftz *= sc;
+                const R ikt = (R)1 / kt;
+                hx = -(ftx + gt * vtx) * ikt; hy = -(fty + gt * vty) * ikt; hz = -(ftz + gt * vtz) * ikt;
+            }
+            fx += fnm * nx + ftx; fy += fnm * ny + fty; fz += fnm * nz + ftz;
+            const R lx = -ri * nx, ly = -ri * ny, lz = -ri * nz;
+            tx += ly * ftz - lz * fty;
+            ty += lz * ftx - lx * ftz;
+            tz += lx * fty - ly * ftx;
+            if (cnt < C.K) {
+                const size_t o = (size_t)cnt * A.stride + s;
+                A.hid_out[o] = pid; A.hx_out[o] = hx; A.hy_out[o] = hy; A.hz_out[o] = hz;
+            }
+            ++cnt;
+        }
+    });
+    if (cnt > C.K) {            // never silent truncation: PST_EOVERFLOW at the next sync
+        atomicExch(&A.flags[0], 1);
+        atomicMax(&A.flags[1], cnt);
+        cnt = C.K;
+    }
+    A.hn_out[s] = cnt;
+    A.fx[s] = fx; A.fy[s] = fy; A.fz[s] = fz;
+    A.tx[s] = tx; A.ty[s] = ty; A.tz[s] = tz;
+}
+
+// semi-implicit Euler for spheres: tag 0 only
+template <class R>
+__global__ void __launch_bounds__(256) k_dem_integrate(int n, R dt, R gx, R gy, R gz, const int32_t* __restrict__ tag, R* __restrict__ x,
+                                                       R* __restrict__ y, R* __restrict__ z, R* __restrict__ u, R* __restrict__ v,
+                                                       R* __restrict__ w, R* __restrict__ wx, R* __restrict__ wy, R* __restrict__ wz,
+                                                       const R* __restrict__ m, const R* __restrict__ inertia, const R* __restrict__ fx,
+                                                       const R* __restrict__ fy, const R* __restrict__ fz, const R* __restrict__ tx,
+                                                       const R* __restrict__ ty, const R* __restrict__ tz) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || tag[s] != 0) return;
+    const R im = (R)1 / m[s], ii = (R)1 / inertia[s];
+    const R un = u[s] + (fx[s] * im + gx) * dt, vn = v[s] + (fy[s] * im + gy) * dt, wn = w[s] + (fz[s] * im + gz) * dt;
+    u[s] = un; v[s] = vn; w[s] = wn;
+    x[s] += un * dt; y[s] += vn * dt; z[s] += wn * dt;
+    wx[s] += tx[s] * ii * dt; wy[s] += ty[s] * ii * dt; wz[s] += tz[s] * ii * dt;
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_dem(pst_ctx* ctx) {
+    if (DIM != 3) return pst_fail(ctx, PST_EINVAL, "DEM needs dim = 3");
+    DemConst<R> C;
+    C.model = (int)pst_param(ctx, "dem_model");
+    C.K = ctx->cfg.max_contacts;
+    C.kn = (R)pst_param(ctx, "kn"); C.gn = (R)pst_param(ctx, "gn"); C.kt = (R)pst_param(ctx, "kt"); C.gt = (R)pst_param(ctx, "gt");
+    C.mu = (R)pst_param(ctx, "mu"); C.dt = (R)pst_param(ctx, "dt");
+    C.Estar = (R)pst_param(ctx, "Estar"); C.Gstar = (R)pst_param(ctx, "Gstar");
+    const double le = std::log(pst_param(ctx, "erest", 1.0));
+    const double be = le / std::sqrt(le * le + 3.14159265358979323846 * 3.14159265358979323846);
+    C.damp_c = (R)(-2.0 * std::sqrt(5.0 / 6.0) * be);
+    PstArray *hn = pst_find(ctx, "hist_n"), *hid = pst_find(ctx, "hist_id"), *hx = pst_find(ctx, "hist_x"), *hy = pst_find(ctx, "hist_y"),
+             *hz = pst_find(ctx, "hist_z");
+    if (!hn) return pst_fail(ctx, PST_ESTATE, "dem_contact needs max_contacts > 0");
+    DemArgs<R> A;
+    A.x = pst_ptr<R>(ctx, "x"); A.y = pst_ptr<R>(ctx, "y"); A.z = pst_ptr<R>(ctx, "z");
+    A.u = pst_ptr<R>(ctx, "u"); A.v = pst_ptr<R>(ctx, "v"); A.w = pst_ptr<R>(ctx, "w");
+    A.wx = pst_ptr<R>(ctx, "wx"); A.wy = pst_ptr<R>(ctx, "wy"); A.wz = pst_ptr<R>(ctx, "wz");
+    A.rad = pst_ptr<R>(ctx, "rad"); A.m = pst_ptr<R>(ctx, "m"); A.id = pst_ptr<uint32_t>(ctx, "id");
+    const int c = hn->cur, d = 1 - hn->cur;
+    A.hn_in = pst_ptr<int32_t>(ctx, hn, 0, c); A.hid_in = pst_ptr<uint32_t>(ctx, hid, 0, c);
+    A.hx_in = pst_ptr<R>(ctx, hx, 0, c); A.hy_in = pst_ptr<R>(ctx, hy, 0, c); A.hz_in = pst_ptr<R>(ctx, hz, 0, c);
+    A.hn_out = pst_ptr<int32_t>(ctx, hn, 0, d); A.hid_out = pst_ptr<uint32_t>(ctx, hid, 0, d);
+    A.hx_out = pst_ptr<R>(ctx, hx, 0, d); A.hy_out = pst_ptr<R>(ctx, hy, 0, d); A.hz_out = pst_ptr<R>(ctx, hz, 0, d);
+    A.fx = pst_ptr<R>(ctx, "fx"); A.fy = pst_ptr<R>(ctx, "fy"); A.fz = pst_ptr<R>(ctx, "fz");
+    A.tx = pst_ptr<R>(ctx, "tx"); A.ty = pst_ptr<R>(ctx, "ty"); A.tz = pst_ptr<R>(ctx, "tz");
+    A.cell_start = ctx->cell_start;
+    A.flags = ctx->d_flags;
+    A.stride = ctx->capacity + 2 * ctx->ghost_cap;
+    A.n = (int)ctx->n;
+    PST_LAUNCH(ctx, (k_dem_forces<R, MORTON>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
+    for (PstArray* a : {hn, hid, hx, hy, hz}) a->cur = d;
+    return PST_OK;
+}
+
+template <class R>
+pst_status launch_dem_integrate(pst_ctx* ctx, double dt) {
+    const int n = (int)ctx->n;
+    PST_LAUNCH(ctx, k_dem_integrate<R>, blocks_for(n, 256), 256, 0, n, (R)dt, (R)pst_param(ctx, "gx"), (R)pst_param(ctx, "gy"),
+               (R)pst_param(ctx, "gz"), pst_ptr<int32_t>(ctx, "tag"), pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), pst_ptr<R>(ctx, "z"),
+               pst_ptr<R>(ctx, "u"), pst_ptr<R>(ctx, "v"), pst_ptr<R>(ctx, "w"), pst_ptr<R>(ctx, "wx"), pst_ptr<R>(ctx, "wy"),
+               pst_ptr<R>(ctx, "wz"), pst_ptr<R>(ctx, "m"), pst_ptr<R>(ctx, "inertia"), pst_ptr<R>(ctx, "fx"), pst_ptr<R>(ctx, "fy"),
+               pst_ptr<R>(ctx, "fz"), pst_ptr<R>(ctx, "tx"), pst_ptr<R>(ctx, "ty"), pst_ptr<R>(ctx, "tz"));
+    return PST_OK;
+}
+
+}  // namespace
+
+pst_status pst_dem_forces(pst_ctx* ctx) {
+    if (ctx->n == 0) return PST_OK;
+    return PST_DISPATCH(ctx, launch_dem, ctx);
+}
+
+pst_status pst_dem_integrate(pst_ctx* ctx, double dt) {
+    if (ctx->n == 0) return PST_OK;
+    return ctx->f64 ? launch_dem_integrate<double>(ctx, dt) : launch_dem_integrate<float>(ctx, dt);
+}

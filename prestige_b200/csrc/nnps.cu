@@ -1,0 +1,293 @@
+// nnps.cu -- cell-linked-list neighbour search on device-resident SoA arrays:
+//   k_keys      cell key (linear, last axis fastest | Morton) per particle          
+//   radix sort  (key, previous index) pairs, only the key bits that are in use      (a8)
+//   k_bounds    cell start table with prefix semantics (start[c+1] = end of cell c) (a8)
+//   k_permute   gather every persistent array into cell order in one pass           (a9)
+//   k_remap_history  move each particle's contact-history row with it               (a9)
+// plus the id-order <-> cell-order reorder kernels behind pst_upload / pst_download and the
+// neighbour/contact-set dump used as the parity hook.
+// No reference code exists for any of this; the loop it feeds is
+// prestige/src/codegen/simple_cpu.rs:7-16.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "pst_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(size_t n, int t = kThreads) { return (unsigned)((n + t - 1) / t); }
+
+__global__ void k_iota(uint32_t* __restrict__ id, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) id[s] = (uint32_t)s;
+}
+
+template <class R, int DIM, bool MORTON>
+__global__ void __launch_bounds__(kThreads) k_keys(GridDev<R> g, int n, const R* __restrict__ x, const R* __restrict__ y,
+                                                   const R* __restrict__ z, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int cx = cell_coord<R>(x[s], g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(y[s], g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    keys[s] = cell_key<DIM, MORTON>(g, cx, cy, cz);
+    vals[s] = (uint32_t)s;
+}
+
+// start[k] = first sorted index whose key is >= k.  Thread s owns the keys in (key[s-1], key[s]].
+__global__ void __launch_bounds__(kThreads) k_bounds(int n, uint32_t ncells, const uint32_t* __restrict__ keys,
+                                                     int32_t* __restrict__ cell_start) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    const long long prev = s == 0 ? -1ll : (long long)keys[s - 1];
+    const long long cur = s == n ? (long long)ncells : (long long)keys[s];
+    for (long long k = prev + 1; k <= cur; ++k) cell_start[k] = s;
+}
+
+constexpr int kMaxPermute = 40;
+struct PermuteList {
+    const void* src[kMaxPermute];
+    void* dst[kMaxPermute];
+    int n8, n4;  // entries [0, n8) are 8-byte, [n8, n8 + n4) are 4-byte
+};
+
+// One thread per destination slot: read the source index once, then issue every gather back to back
+// (independent loads -> deep memory-level parallelism), stores are fully coalesced.
+__global__ void __launch_bounds__(kThreads) k_permute(PermuteList L, int n, const uint32_t* __restrict__ perm) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t p = perm[s];
+#pragma unroll 4
+    for (int a = 0; a < L.n8; ++a)
+        reinterpret_cast<unsigned long long*>(L.dst[a])[s] = __ldg(reinterpret_cast<const unsigned long long*>(L.src[a]) + p);
+#pragma unroll 4
+    for (int a = L.n8; a < L.n8 + L.n4; ++a)
+        reinterpret_cast<uint32_t*>(L.dst[a])[s] = __ldg(reinterpret_cast<const uint32_t*>(L.src[a]) + p);
+}
+
+// Contact history follows its particle.  Only the slots in use are moved (slot-major layout, so
+// slot k of consecutive particles is contiguous).
+template <class R>
+__global__ void __launch_bounds__(kThreads) k_remap_history(int n, size_t stride, const uint32_t* __restrict__ perm,
+                                                            const int32_t* __restrict__ hn_s, const uint32_t* __restrict__ hid_s,
+                                                            const R* __restrict__ hx_s, const R* __restrict__ hy_s,
+                                                            const R* __restrict__ hz_s, int32_t* __restrict__ hn_d,
+                                                            uint32_t* __restrict__ hid_d, R* __restrict__ hx_d,
+                                                            R* __restrict__ hy_d, R* __restrict__ hz_d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t p = perm[s];
+    const int cnt = hn_s[p];
+    hn_d[s] = cnt;
+    for (int k = 0; k < cnt; ++k) {
+        const size_t o = (size_t)k * stride;
+        hid_d[o + s] = hid_s[o + p];
+        hx_d[o + s] = hx_s[o + p];
+        hy_d[o + s] = hy_s[o + p];
+        hz_d[o + s] = hz_s[o + p];
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_gather_by_id(int n, const uint32_t* __restrict__ id, const T* __restrict__ stage,
+                                                           T* __restrict__ dst) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[s] = stage[id[s]];
+}
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_scatter_by_id(int n, const uint32_t* __restrict__ id, const T* __restrict__ src,
+                                                            T* __restrict__ stage) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) stage[id[s]] = src[s];
+}
+
+// Neighbour / contact set dump (parity hook).  mode 0: r2 < (kfac*s_i)^2, s = h.  mode 1: r2 < (s_i+s_j)^2, s = rad.
+template <class R, int DIM, bool MORTON>
+__global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, int mode, R kfac, const int32_t* __restrict__ cell_start,
+                                                         const R* __restrict__ x, const R* __restrict__ y, const R* __restrict__ z,
+                                                         const R* __restrict__ sz, const uint32_t* __restrict__ id,
+                                                         uint32_t* __restrict__ oi, uint32_t* __restrict__ oj,
+                                                         unsigned long long cap, unsigned long long* __restrict__ counter) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const R xi = x[s], yi = y[s], zi = DIM == 3 ? z[s] : (R)0, si = sz[s];
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    const uint32_t idi = id[s];
+    for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
+        for (int j = b; j < e; ++j) {
+            if (j == s) continue;
+            const R r2 = dist2<DIM, R>(xi - x[j], yi - y[j], DIM == 3 ? zi - z[j] : (R)0);
+            const R rc = mode == 0 ? mul_rn(kfac, si) : add_rn(si, sz[j]);
+            if (r2 < mul_rn(rc, rc)) {
+                const unsigned long long k = atomicAdd(counter, 1ull);
+                if (k < cap) { oi[k] = idi; oj[k] = id[j]; }
+            }
+        }
+    });
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_keys(pst_ctx* ctx) {
+    const int n = (int)ctx->n;
+    PST_LAUNCH(ctx, (k_keys<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n,
+               pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, ctx->keys_in, ctx->vals_in);
+    return PST_OK;
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_dump(pst_ctx* ctx, int mode, const void* sz, uint32_t* oi, uint32_t* oj, size_t cap) {
+    const int n = (int)ctx->n;
+    PST_LAUNCH(ctx, (k_dump_pairs<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n, mode,
+               (R)pst_param(ctx, "kfac", 2.0), ctx->cell_start, pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"),
+               DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, (const R*)sz, pst_ptr<uint32_t>(ctx, "id"), oi, oj,
+               (unsigned long long)cap, ctx->d_counters);
+    return PST_OK;
+}
+
+template <class R>
+pst_status launch_remap(pst_ctx* ctx) {
+    PstArray* hn = pst_find(ctx, "hist_n");
+    if (!hn) return PST_OK;
+    PstArray *hid = pst_find(ctx, "hist_id"), *hx = pst_find(ctx, "hist_x"), *hy = pst_find(ctx, "hist_y"), *hz = pst_find(ctx, "hist_z");
+    const int n = (int)ctx->n;
+    const size_t stride = ctx->capacity + 2 * ctx->ghost_cap;
+    const int c = hn->cur, d = 1 - hn->cur;
+    PST_LAUNCH(ctx, (k_remap_history<R>), blocks_for(n), kThreads, 0, n, stride, ctx->vals_out,
+               pst_ptr<int32_t>(ctx, hn, 0, c), pst_ptr<uint32_t>(ctx, hid, 0, c), pst_ptr<R>(ctx, hx, 0, c),
+               pst_ptr<R>(ctx, hy, 0, c), pst_ptr<R>(ctx, hz, 0, c), pst_ptr<int32_t>(ctx, hn, 0, d),
+               pst_ptr<uint32_t>(ctx, hid, 0, d), pst_ptr<R>(ctx, hx, 0, d), pst_ptr<R>(ctx, hy, 0, d), pst_ptr<R>(ctx, hz, 0, d));
+    for (PstArray* a : {hn, hid, hx, hy, hz}) a->cur = d;
+    return PST_OK;
+}
+
+bool is_history(const PstArray& a) { return a.name.rfind("hist_", 0) == 0; }
+
+}  // namespace
+
+pst_status pst_nnps_alloc(pst_ctx* ctx) {
+    const size_t cap = ctx->capacity + 2 * ctx->ghost_cap;
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->keys_in, cap * 4));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->keys_out, cap * 4));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->vals_in, cap * 4));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->vals_out, cap * 4));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)ctx->grid.ncells + 1) * 4));
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)ctx->grid.ncells + 1) * 4, ctx->stream));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->stage, cap * 8));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_flags, 8 * sizeof(int32_t)));
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 8 * sizeof(int32_t), cudaHostAllocDefault));
+    PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    ctx->sort_tmp_bytes = 0;
+    PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, ctx->keys_in, ctx->keys_out, ctx->vals_in,
+                                                  ctx->vals_out, (int)cap, 0, 32, ctx->stream));
+    PST_CUDA(ctx, cudaMalloc(&ctx->sort_tmp, ctx->sort_tmp_bytes));
+    return PST_OK;
+}
+
+pst_status pst_iota_ids(pst_ctx* ctx) {
+    if (ctx->n == 0) return PST_OK;
+    PST_LAUNCH(ctx, k_iota, blocks_for(ctx->n), kThreads, 0, pst_ptr<uint32_t>(ctx, "id"), (int)ctx->n);
+    return PST_OK;
+}
+
+pst_status pst_nnps_build(pst_ctx* ctx) {
+    if (!pst_find(ctx, "x")) return pst_fail(ctx, PST_ESTATE, "context has no position arrays (physics = PST_PHYS_NONE)");
+    const int n = (int)ctx->n;
+    ctx->n_ghost_l = ctx->n_ghost_r = 0;
+    if (n > 0) {
+        PST_TRY(PST_DISPATCH(ctx, launch_keys, ctx));
+        size_t tmp = ctx->sort_tmp_bytes;
+        PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tmp, ctx->keys_in, ctx->keys_out, ctx->vals_in, ctx->vals_out,
+                                                      n, 0, ctx->grid.key_bits, ctx->stream));
+        ctx->launches += (ctx->grid.key_bits + 7) / 8 + 2;  // CUB onesweep: histogram + scan + one pass per 8 bits
+    }
+    PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, ctx->grid.ncells, ctx->keys_out, ctx->cell_start);
+    if (n > 0) {
+        PermuteList L;
+        L.n8 = L.n4 = 0;
+        std::vector<PstArray*> moved;
+        for (int pass = 0; pass < 2; ++pass)
+            for (auto& a : ctx->arrays) {
+                if (!(a.flags & PST_ARRAY_PERSISTENT) || is_history(a)) continue;
+                if ((pass == 0) != (a.esize == 8)) continue;
+                for (int r = 0; r < a.rows; ++r) {
+                    const int k = L.n8 + L.n4;
+                    if (k >= kMaxPermute) return pst_fail(ctx, PST_EINVAL, "too many persistent arrays (max %d)", kMaxPermute);
+                    L.src[k] = pst_ptr<char>(ctx, &a, r, a.cur);
+                    L.dst[k] = pst_ptr<char>(ctx, &a, r, 1 - a.cur);
+                    (pass == 0 ? L.n8 : L.n4)++;
+                }
+                moved.push_back(&a);
+            }
+        PST_LAUNCH(ctx, k_permute, blocks_for(n), kThreads, 0, L, n, ctx->vals_out);
+        for (PstArray* a : moved) a->cur = 1 - a->cur;
+        if (ctx->f64) PST_TRY(launch_remap<double>(ctx)); else PST_TRY(launch_remap<float>(ctx));
+    }
+    ctx->ordered = true;
+    ctx->nbrs_valid = true;
+    ctx->eos_valid = false;
+    return PST_OK;
+}
+
+pst_status pst_reorder_upload(pst_ctx* ctx, PstArray* a, int row, size_t n) {
+    const uint32_t* id = pst_ptr<uint32_t>(ctx, "id");
+    if (a->esize == 8)
+        PST_LAUNCH(ctx, k_gather_by_id<unsigned long long>, blocks_for(n), kThreads, 0, (int)n, id,
+                   (const unsigned long long*)ctx->stage, pst_ptr<unsigned long long>(ctx, a, row));
+    else
+        PST_LAUNCH(ctx, k_gather_by_id<uint32_t>, blocks_for(n), kThreads, 0, (int)n, id, (const uint32_t*)ctx->stage,
+                   pst_ptr<uint32_t>(ctx, a, row));
+    return PST_OK;
+}
+
+pst_status pst_reorder_download(pst_ctx* ctx, PstArray* a, int row, size_t n) {
+    const uint32_t* id = pst_ptr<uint32_t>(ctx, "id");
+    if (a->esize == 8)
+        PST_LAUNCH(ctx, k_scatter_by_id<unsigned long long>, blocks_for(n), kThreads, 0, (int)n, id,
+                   pst_ptr<unsigned long long>(ctx, a, row), (unsigned long long*)ctx->stage);
+    else
+        PST_LAUNCH(ctx, k_scatter_by_id<uint32_t>, blocks_for(n), kThreads, 0, (int)n, id, pst_ptr<uint32_t>(ctx, a, row),
+                   (uint32_t*)ctx->stage);
+    return PST_OK;
+}
+
+pst_status pst_nnps_dump_pairs(pst_ctx* ctx, int mode, uint32_t* hi, uint32_t* hj, size_t cap, size_t* n_pairs) {
+    if (mode != 0 && mode != 1) return pst_fail(ctx, PST_EINVAL, "dump_pairs mode must be 0 (neighbours) or 1 (contacts)");
+    PstArray* sa = pst_find(ctx, mode == 0 ? "h" : "rad");
+    if (!sa) return pst_fail(ctx, PST_ESTATE, "dump_pairs mode %d needs array '%s'", mode, mode == 0 ? "h" : "rad");
+    uint32_t *di = nullptr, *dj = nullptr;
+    if (cap) {
+        if (cudaMalloc((void**)&di, cap * 4) != cudaSuccess || cudaMalloc((void**)&dj, cap * 4) != cudaSuccess) {
+            cudaFree(di);
+            return pst_fail(ctx, PST_ENOMEM, "pair buffer of %zu entries does not fit on the device", cap);
+        }
+    }
+    pst_status s = PST_OK;
+    cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream);
+    if (ctx->n > 0) {
+        s = PST_DISPATCH(ctx, launch_dump, ctx, mode, pst_ptr<char>(ctx, sa), di, dj, cap);
+    }
+    if (s == PST_OK) {
+        cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) s = pst_fail(ctx, PST_ECUDA, "dump_pairs: %s", cudaGetErrorString(e));
+    }
+    if (s == PST_OK) {
+        const size_t cnt = (size_t)ctx->h_counters[0];
+        *n_pairs = cnt;
+        const size_t m = cnt < cap ? cnt : cap;
+        if (m) {
+            cudaMemcpy(hi, di, m * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hj, dj, m * 4, cudaMemcpyDeviceToHost);
+        }
+        if (cnt > cap) s = pst_fail(ctx, PST_EOVERFLOW, "%zu pairs > buffer capacity %zu", cnt, cap);
+    }
+    cudaFree(di);
+    cudaFree(dj);
+    return s;
+}

@@ -1,0 +1,455 @@
+// wcsph.cu -- weakly-compressible SPH: Tait EOS, continuity, momentum (+ artificial viscosity,
+// gravity), semi-implicit Euler stage.  Formulation: SURVEY.md Appendix A.2 / DESIGN.md.
+// No reference code exists for the physics; what the reference fixes is
+// the loop shape -- gather into [i], bodies of a fused set share one i,j loop
+// (prestige/src/codegen/simple_cpu.rs:7-16, prestige/src/equations/fuse.rs:14-40).
+//
+// Two pair kernels, both computing continuity and/or momentum in ONE j loop:
+//   k_wcsph_gather  one thread per particle, walks its 9 (3D) / 3 (2D) contiguous candidate runs
+//                   straight from global memory.  Any key mode, any occupancy.  (option force_kernel=0)
+//   k_wcsph_tiled   one CTA per tile of A x B cell columns x G cells along the fast axis.  The
+//                   (A+2)(B+2) candidate runs are staged ONCE in shared memory (coalesced loads of the
+//                   sorted SoA arrays), then every thread (a) scans its candidates with the exact,
+//                   FMA-free cutoff test and compacts the hits into a private list, (b) evaluates the
+//                   expensive pair body only for the hits, with all lanes busy.  Linear keys only.
+#include "pst_internal.h"
+
+namespace {
+
+constexpr int kThreads = 128;
+inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <class R>
+struct WcsphConst {
+    R kfac, rho0, c0, gamma, B, alpha_c0, beta, g[3];
+    int gamma_is_7;
+};
+
+template <class R>
+WcsphConst<R> make_const(pst_ctx* ctx) {
+    WcsphConst<R> C;
+    const double rho0 = pst_param(ctx, "rho0"), c0 = pst_param(ctx, "c0"), gamma = pst_param(ctx, "gamma");
+    C.kfac = (R)pst_param(ctx, "kfac", 2.0);
+    C.rho0 = (R)rho0; C.c0 = (R)c0; C.gamma = (R)gamma;
+    C.B = (R)(rho0 * c0 * c0 / gamma);
+    C.alpha_c0 = (R)(pst_param(ctx, "alpha") * c0);
+    C.beta = (R)pst_param(ctx, "beta");
+    C.g[0] = (R)pst_param(ctx, "gx"); C.g[1] = (R)pst_param(ctx, "gy"); C.g[2] = (R)pst_param(ctx, "gz");
+    C.gamma_is_7 = gamma == 7.0;
+    return C;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EOS: p = B((rho/rho0)^gamma - 1), and p/rho^2 which is what the momentum body consumes.
+// Runs over owned + ghost particles.
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, const R* __restrict__ rho, R* __restrict__ p,
+                                             R* __restrict__ por2) {
+    const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= hi) return;
+    const R r = rho[s];
+    const R q = r / C.rho0;
+    R pw;
+    if (C.gamma_is_7) { const R q2 = q * q, q4 = q2 * q2; pw = q4 * q2 * q; }
+    else pw = pow(q, C.gamma);
+    const R pr = C.B * (pw - (R)1);
+    p[s] = pr;
+    por2[s] = pr / (r * r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the pair body (continuity then momentum, the order fuse() keeps: fuse.rs:18,30)
+// ---------------------------------------------------------------------------------------------
+template <class R, int DIM>
+struct IState {         // everything about particle i the body needs, in registers
+    R x, y, z, u, v, w, rho, por2, h, half_inv_h, gfc, eta2, rc2;
+};
+template <class R>
+struct Acc { R au, av, aw, arho; };
+
+template <class R, int DIM>
+__device__ __forceinline__ void load_i(IState<R, DIM>& I, const WcsphConst<R>& C, R x, R y, R z, R u, R v, R w, R rho, R por2, R h) {
+    I.x = x; I.y = y; I.z = z; I.u = u; I.v = v; I.w = w; I.rho = rho; I.por2 = por2; I.h = h;
+    I.half_inv_h = (R)0.5 / h;
+    const R pi = (R)3.14159265358979323846;
+    const R ad = DIM == 3 ? (R)(21.0 / 16.0) / (pi * h * h * h) : (R)(7.0 / 4.0) / (pi * h * h);
+    I.gfc = (R)-5 * ad / (h * h);       // (dW/dq)/(h r) = gfc * (1 - q/2)^3
+    I.eta2 = (R)0.01 * h * h;
+    const R rc = mul_rn(C.kfac, h);
+    I.rc2 = mul_rn(rc, rc);
+}
+
+// caller has already established 0 < r2 < rc2 with the exact test
+template <class R, int DIM, bool CONT, bool MOM>
+__device__ __forceinline__ void pair_body(const WcsphConst<R>& C, const IState<R, DIM>& I, R dx, R dy, R dz, R r2, R uj, R vj, R wj,
+                                          R rhoj, R mj, R por2j, Acc<R>& a) {
+    const R r = sqrt(r2);
+    const R t = (R)1 - r * I.half_inv_h;
+    const R gf = I.gfc * (t * t * t);
+    const R du = I.u - uj, dv = I.v - vj, dw = DIM == 3 ? I.w - wj : (R)0;
+    R vx = du * dx + dv * dy;
+    if (DIM == 3) vx += dw * dz;
+    const R mgf = mj * gf;
+    if (CONT) a.arho += mgf * vx;
+    if (MOM) {
+        R Pi = (R)0;
+        if (vx < (R)0) {
+            const R mu = I.h * vx / (r2 + I.eta2);
+            Pi = (C.beta * mu - C.alpha_c0) * mu / ((R)0.5 * (I.rho + rhoj));
+        }
+        const R c = -mgf * (I.por2 + por2j + Pi);
+        a.au += c * dx;
+        a.av += c * dy;
+        if (DIM == 3) a.aw += c * dz;
+    }
+}
+
+template <class R>
+struct ForceArgs {
+    const R *x, *y, *z, *u, *v, *w, *rho, *m, *h, *por2;
+    R *au, *av, *aw, *arho;
+    const int32_t* cell_start;
+    int n;
+};
+
+template <class R, int DIM, bool CONT, bool MOM>
+__device__ __forceinline__ void store_acc(const ForceArgs<R>& A, const WcsphConst<R>& C, int s, const Acc<R>& a) {
+    if (CONT) A.arho[s] = a.arho;
+    if (MOM) {
+        A.au[s] = a.au + C.g[0];
+        A.av[s] = a.av + C.g[1];
+        if (DIM == 3) A.aw[s] = a.aw + C.g[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 0: per-particle gather
+// ---------------------------------------------------------------------------------------------
+template <class R, int DIM, bool MORTON, bool CONT, bool MOM>
+__device__ __forceinline__ void gather_one(const GridDev<R>& g, const WcsphConst<R>& C, const ForceArgs<R>& A, int s) {
+    IState<R, DIM> I;
+    load_i<R, DIM>(I, C, A.x[s], A.y[s], DIM == 3 ? A.z[s] : (R)0, A.u[s], A.v[s], DIM == 3 ? A.w[s] : (R)0, A.rho[s], A.por2[s], A.h[s]);
+    const int cx = cell_coord<R>(I.x, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(I.y, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    Acc<R> a{0, 0, 0, 0};
+    for_each_run<DIM, MORTON>(g, A.cell_start, cx, cy, cz, [&](int b, int e) {
+        for (int j = b; j < e; ++j) {
+            const R dx = I.x - A.x[j], dy = I.y - A.y[j], dz = DIM == 3 ? I.z - A.z[j] : (R)0;
+            const R r2 = dist2<DIM, R>(dx, dy, dz);
+            if (r2 < I.rc2 && r2 > (R)0 && j != s)
+                pair_body<R, DIM, CONT, MOM>(C, I, dx, dy, dz, r2, A.u[j], A.v[j], DIM == 3 ? A.w[j] : (R)0, A.rho[j], A.m[j], A.por2[j], a);
+        }
+    });
+    store_acc<R, DIM, CONT, MOM>(A, C, s, a);
+}
+
+template <class R, int DIM, bool MORTON, bool CONT, bool MOM>
+__global__ void __launch_bounds__(kThreads) k_wcsph_gather(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n) return;
+    gather_one<R, DIM, MORTON, CONT, MOM>(g, C, A, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 1: shared-memory tiles + per-thread hit lists
+// ---------------------------------------------------------------------------------------------
+struct TileShape {
+    int G;          // cells per tile along the fast axis
+    int tiles[3];   // tile grid: [0] columns-x, [1] columns-y (1 in 2D), [2] fast axis
+    int jcap;       // staged-candidate capacity (elements)
+    int lcap;       // hit-list capacity per thread
+};
+
+template <int DIM, int A, int B>
+struct TileDims {
+    static constexpr int BB = DIM == 3 ? B : 1;
+    static constexpr int NI = A * BB;                              // i columns
+    static constexpr int NR = (A + 2) * (DIM == 3 ? BB + 2 : 1);   // staged runs
+    static constexpr int RY = DIM == 3 ? BB + 2 : 1;               // runs along y
+};
+
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
+__global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
+    using D = TileDims<DIM, TA, TB>;
+    constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = T.G, W = G + 3;  // W boundaries per run
+    // ---- shared memory carve-up
+    int* s_cs = reinterpret_cast<int*>(smem_raw);            // NR * W   virtual cell boundaries
+    int* s_gbeg = s_cs + NR * W;                              // NR       global begin of each run
+    int* s_voff = s_gbeg + NR;                                // NR + 1   virtual offset of each run
+    int* s_ibeg = s_voff + NR + 1;                            // NI       global begin of each i segment
+    int* s_ipre = s_ibeg + NI;                                // NI + 1   prefix of i counts
+    size_t off = ((size_t)(NR * W + NR + NR + 1 + NI + NI + 1) * sizeof(int) + 15) & ~(size_t)15;
+    R* s_x = reinterpret_cast<R*>(smem_raw + off);
+    const int JC = T.jcap;
+    R* s_y = s_x + JC; R* s_z = s_y + JC; R* s_u = s_z + JC; R* s_v = s_u + JC; R* s_w = s_v + JC;
+    R* s_rho = s_w + JC; R* s_m = s_rho + JC; R* s_por2 = s_m + JC;
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_por2 + JC);   // lcap * NT
+
+    const int tid = threadIdx.x;
+    // ---- which tile
+    int b = blockIdx.x;
+    const int tf = b % T.tiles[2]; b /= T.tiles[2];
+    const int ty = DIM == 3 ? b % T.tiles[1] : 0; if (DIM == 3) b /= T.tiles[1];
+    const int tx = b;
+    const int cx0 = tx * TA, cy0 = ty * BB, f0 = tf * G;
+    const int nf = DIM == 3 ? g.n[2] : g.n[1];   // cells along the fast axis
+    const int ncx = g.n[0], ncy = DIM == 3 ? g.n[1] : 1;
+
+    // ---- cell boundaries of every staged run (global indices first)
+    for (int t = tid; t < NR * W; t += NT) {
+        const int q = t / W, tt = t - q * W;
+        const int rx = q / RY, ry = q - rx * RY;
+        const int cx = cx0 - 1 + rx, cy = DIM == 3 ? cy0 - 1 + ry : 0;
+        int gi = 0;
+        if (cx >= 0 && cx < ncx && cy >= 0 && cy < ncy) {
+            const int col = DIM == 3 ? cx * ncy + cy : cx;
+            const int f = min(max(f0 - 1 + tt, 0), nf);
+            gi = A.cell_start[(size_t)col * nf + f];
+        } else {
+            gi = 0;  // column outside the grid: all boundaries equal -> empty run
+        }
+        s_cs[t] = gi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int q = 0; q < NR; ++q) {
+            s_gbeg[q] = s_cs[q * W];
+            s_voff[q] = acc;
+            acc += s_cs[q * W + W - 1] - s_cs[q * W];
+        }
+        s_voff[NR] = acc;
+        // i segments: tile columns, fast cells [f0, f0 + G)  == boundaries tt = 1 .. G+1 of the centre runs
+        int ia = 0;
+        for (int c = 0; c < NI; ++c) {
+            const int lx = c / BB, ly = c - lx * BB;
+            const int q = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
+            const int cx = cx0 + lx, cy = cy0 + ly;
+            int cnt = 0, beg = 0;
+            if (cx >= g.cx_lo && cx <= g.cx_hi && cy < ncy) { beg = s_cs[q * W + 1]; cnt = s_cs[q * W + G + 1] - beg; }  // ghost layers are never i
+            s_ibeg[c] = beg;
+            s_ipre[c] = ia;
+            ia += cnt;
+        }
+        s_ipre[NI] = ia;
+    }
+    __syncthreads();
+    const int ni = s_ipre[NI];
+    if (ni == 0) return;                      // empty tile (uniform exit)
+    const int M = s_voff[NR];
+    if (M > JC) {
+        // tile denser than the staging buffer: exact per-particle gather for its particles
+        for (int ii = tid; ii < ni; ii += NT) {
+            int c = 0;
+            while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
+            gather_one<R, DIM, false, CONT, MOM>(g, C, A, s_ibeg[c] + (ii - s_ipre[c]));
+        }
+        return;
+    }
+    // ---- rebase boundaries to virtual offsets
+    for (int t = tid; t < NR * W; t += NT) {
+        const int q = t / W;
+        s_cs[t] = s_voff[q] + (s_cs[t] - s_gbeg[q]);
+    }
+    // ---- stage candidates: flattened over the concatenated runs, coalesced inside each run
+    for (int v = tid; v < M; v += NT) {
+        int q = 0;
+        while (q + 1 < NR && v >= s_voff[q + 1]) ++q;
+        const int gj = s_gbeg[q] + (v - s_voff[q]);
+        s_x[v] = A.x[gj]; s_y[v] = A.y[gj]; if (DIM == 3) s_z[v] = A.z[gj];
+        s_u[v] = A.u[gj]; s_v[v] = A.v[gj]; if (DIM == 3) s_w[v] = A.w[gj];
+        s_rho[v] = A.rho[gj]; s_m[v] = A.m[gj]; s_por2[v] = A.por2[gj];
+    }
+    __syncthreads();
+
+    const int LC = T.lcap;
+    for (int ii0 = 0; ii0 < ni; ii0 += NT) {   // uniform trip count: rounds of NT particles
+        const int ii = ii0 + tid;
+        const bool active = ii < ni;
+        int c = 0, gi = 0, lx = 0, ly = 0, lf = 0;
+        IState<R, DIM> I;
+        Acc<R> a{0, 0, 0, 0};
+        if (active) {
+            while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
+            gi = s_ibeg[c] + (ii - s_ipre[c]);
+            lx = c / BB; ly = c - lx * BB;
+            load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
+                           A.por2[gi], A.h[gi]);
+            const int cf = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : cell_coord<R>(I.y, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+            lf = cf - f0;   // 0 .. G-1
+        }
+        // scan cursor over this particle's 9 (3) runs
+        int run = 0, jv = 0, jend = 0;
+        constexpr int NRUN = DIM == 3 ? 9 : 3;
+        auto open_run = [&](int k) {
+            const int ax = DIM == 3 ? k / 3 : k, ay = DIM == 3 ? k - ax * 3 : 0;
+            const int q = (lx + ax) * RY + (DIM == 3 ? ly + ay : 0);
+            jv = s_cs[q * W + lf];
+            jend = s_cs[q * W + lf + 3];
+        };
+        bool done = !active;
+        if (active) open_run(0);
+        while (true) {
+            // ---- phase 1: exact cutoff test on staged candidates, compact hits into the private list
+            int cnt = 0;
+            if (!done) {
+                while (true) {
+                    while (jv < jend && cnt < LC) {
+                        const R dx = I.x - s_x[jv], dy = I.y - s_y[jv], dz = DIM == 3 ? I.z - s_z[jv] : (R)0;
+                        const R r2 = dist2<DIM, R>(dx, dy, dz);
+                        if (r2 < I.rc2 && r2 > (R)0) { s_list[cnt * NT + tid] = (unsigned short)jv; ++cnt; }
+                        ++jv;
+                    }
+                    if (jv < jend) break;          // list full: drain, then resume here
+                    if (++run == NRUN) { done = true; break; }
+                    open_run(run);
+                }
+            }
+            // ---- phase 2: the pair body on hits only
+            for (int k = 0; k < cnt; ++k) {
+                const int j = s_list[k * NT + tid];
+                const R dx = I.x - s_x[j], dy = I.y - s_y[j], dz = DIM == 3 ? I.z - s_z[j] : (R)0;
+                const R r2 = dist2<DIM, R>(dx, dy, dz);
+                pair_body<R, DIM, CONT, MOM>(C, I, dx, dy, dz, r2, s_u[j], s_v[j], DIM == 3 ? s_w[j] : (R)0, s_rho[j], s_m[j], s_por2[j], a);
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+        if (active) store_acc<R, DIM, CONT, MOM>(A, C, gi, a);
+    }
+}
+
+template <class R>
+ForceArgs<R> make_args(pst_ctx* ctx) {
+    ForceArgs<R> A;
+    A.x = pst_ptr<R>(ctx, "x"); A.y = pst_ptr<R>(ctx, "y"); A.z = pst_ptr<R>(ctx, "z");
+    A.u = pst_ptr<R>(ctx, "u"); A.v = pst_ptr<R>(ctx, "v"); A.w = pst_ptr<R>(ctx, "w");
+    A.rho = pst_ptr<R>(ctx, "rho"); A.m = pst_ptr<R>(ctx, "m"); A.h = pst_ptr<R>(ctx, "h"); A.por2 = pst_ptr<R>(ctx, "por2");
+    A.au = pst_ptr<R>(ctx, "au"); A.av = pst_ptr<R>(ctx, "av"); A.aw = pst_ptr<R>(ctx, "aw"); A.arho = pst_ptr<R>(ctx, "arho");
+    A.cell_start = ctx->cell_start;
+    A.n = (int)ctx->n;
+    return A;
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_gather(pst_ctx* ctx, bool cont, bool mom) {
+    const GridDev<R> g = make_grid_dev<R>(ctx->grid);
+    const WcsphConst<R> C = make_const<R>(ctx);
+    const ForceArgs<R> A = make_args<R>(ctx);
+    const unsigned grid = blocks_for(ctx->n, kThreads);
+    if (cont && mom) PST_LAUNCH(ctx, (k_wcsph_gather<R, DIM, MORTON, true, true>), grid, kThreads, 0, g, C, A);
+    else if (cont) PST_LAUNCH(ctx, (k_wcsph_gather<R, DIM, MORTON, true, false>), grid, kThreads, 0, g, C, A);
+    else PST_LAUNCH(ctx, (k_wcsph_gather<R, DIM, MORTON, false, true>), grid, kThreads, 0, g, C, A);
+    return PST_OK;
+}
+
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
+pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
+    auto kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM>;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)T.tiles[0] * T.tiles[1] * T.tiles[2];
+    PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), make_args<R>(ctx), T);
+    return PST_OK;
+}
+
+template <class R, int DIM>
+pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
+    constexpr int TA = 2, TB = 2, NT = 256;
+    using D = TileDims<DIM, TA, TB>;
+    const PstGrid& g = ctx->grid;
+    const int nf = DIM == 3 ? g.n[2] : g.n[1];
+    // tile depth along the fast axis: fill NT threads at the mean occupancy of the occupied cells
+    double ppc = pst_param(ctx, "_ppc", 0.0);
+    if (!(ppc > 0)) ppc = DIM == 3 ? 14.0 : 6.0;
+    const int user_G = pst_option(ctx, "tile_g", 0);
+    int G = user_G > 0 ? user_G : (int)std::max(1.0, std::floor(0.95 * NT / (D::NI * ppc)));
+    G = std::min(G, std::max(1, nf));
+    TileShape T;
+    T.G = G;
+    T.tiles[0] = (g.n[0] + TA - 1) / TA;
+    T.tiles[1] = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
+    T.tiles[2] = (nf + G - 1) / G;
+    T.lcap = pst_option(ctx, "tile_lcap", DIM == 3 ? 80 : 32);
+    const size_t ints = ((size_t)(D::NR * (G + 3) + D::NR + D::NR + 1 + D::NI + D::NI + 1) * sizeof(int) + 15) & ~(size_t)15;
+    const size_t list = (size_t)T.lcap * NT * sizeof(unsigned short);
+    const size_t budget = (size_t)pst_option(ctx, "tile_smem_kb", 200) * 1024;
+    if (ints + list + 9 * sizeof(R) * 64 > budget) return pst_fail(ctx, PST_EINVAL, "tile_smem_kb too small");
+    int jcap = (int)((budget - ints - list) / (9 * sizeof(R)));
+    jcap = std::min(jcap, 65535) & ~1;   // hit lists hold 16-bit staged indices
+    T.jcap = jcap;
+    const size_t smem = ints + (size_t)jcap * 9 * sizeof(R) + list;
+    if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, true, true>(ctx, T, smem);
+    if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, true, false>(ctx, T, smem);
+    return launch_tiled_k<R, DIM, TA, TB, NT, false, true>(ctx, T, smem);
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
+    const int variant = pst_option(ctx, "force_kernel", 1);
+    if (variant == 1 && !MORTON) return launch_tiled<R, DIM>(ctx, cont, mom);
+    return launch_gather<R, DIM, MORTON>(ctx, cont, mom);
+}
+
+// semi-implicit Euler stage: fluid (tag 0): v += a dt, x += v dt;
+// every particle: rho += arho dt.  Boundary particles (tag 1) keep position and velocity.
+template <class R, int DIM>
+__global__ void __launch_bounds__(256) k_integrate(int n, R dt, const int32_t* __restrict__ tag, R* __restrict__ x, R* __restrict__ y,
+                                                   R* __restrict__ z, R* __restrict__ u, R* __restrict__ v, R* __restrict__ w,
+                                                   R* __restrict__ rho, const R* __restrict__ au, const R* __restrict__ av,
+                                                   const R* __restrict__ aw, const R* __restrict__ arho) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    rho[s] += arho[s] * dt;
+    if (tag[s] != 0) return;
+    const R un = u[s] + au[s] * dt, vn = v[s] + av[s] * dt;
+    u[s] = un; v[s] = vn;
+    x[s] += un * dt; y[s] += vn * dt;
+    if (DIM == 3) {
+        const R wn = w[s] + aw[s] * dt;
+        w[s] = wn;
+        z[s] += wn * dt;
+    }
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_integrate(pst_ctx* ctx, double dt) {
+    const int n = (int)ctx->n;
+    PST_LAUNCH(ctx, (k_integrate<R, DIM>), blocks_for(n, 256), 256, 0, n, (R)dt, pst_ptr<int32_t>(ctx, "tag"), pst_ptr<R>(ctx, "x"),
+               pst_ptr<R>(ctx, "y"), pst_ptr<R>(ctx, "z"), pst_ptr<R>(ctx, "u"), pst_ptr<R>(ctx, "v"), pst_ptr<R>(ctx, "w"),
+               pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "au"), pst_ptr<R>(ctx, "av"), pst_ptr<R>(ctx, "aw"), pst_ptr<R>(ctx, "arho"));
+    return PST_OK;
+}
+
+template <class R>
+pst_status launch_eos(pst_ctx* ctx) {
+    const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r;
+    if (hi <= lo) return PST_OK;
+    PST_LAUNCH(ctx, k_eos<R>, blocks_for(hi - lo, 256), 256, 0, make_const<R>(ctx), lo, hi, pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "p"),
+               pst_ptr<R>(ctx, "por2"));
+    return PST_OK;
+}
+
+}  // namespace
+
+pst_status pst_wcsph_eos(pst_ctx* ctx) {
+    PST_TRY(ctx->f64 ? launch_eos<double>(ctx) : launch_eos<float>(ctx));
+    ctx->eos_valid = true;
+    return PST_OK;
+}
+
+pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum) {
+    if (ctx->n == 0) return PST_OK;
+    return PST_DISPATCH(ctx, launch_forces, ctx, continuity, momentum);
+}
+
+pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt) {
+    if (ctx->n == 0) return PST_OK;
+    return PST_DISPATCH(ctx, launch_integrate, ctx, dt);
+}

@@ -1,0 +1,30 @@
+"""Regenerates the golden vectors in this directory from the CPU oracle (oracle/oracle.cpp).
+
+The reference (dineshadepu/prestige) has no implementation of this path and no fixtures, so these
+vectors pin THIS repo's written contract, not reference outputs: "parity unpinned".
+Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import oracle as orc            # noqa: E402
+from prestige_b200 import synth             # noqa: E402
+
+b = synth.wcsph_block_3d(9, 8, 7).shuffled()
+r = orc.wcsph(3, b.params, b.arrays)
+pr, _ = orc.pairs(3, b.arrays["x"], b.arrays["y"], b.arrays["z"], b.arrays["h"])
+np.savez_compressed(os.path.join(HERE, "wcsph3d_small.npz"), x=b.arrays["x"], pairs=pr, **r)
+
+d = synth.dem_column_3d(6).shuffled()
+f1, h1, _ = orc.dem(d.params, 12, d.arrays)
+f2, h2, _ = orc.dem(d.params, 12, d.arrays, hist=h1)
+np.savez_compressed(os.path.join(HERE, "dem3d_small.npz"), **f2, **h2)
+
+c = synth.wcsph_dambreak_2d(dx=0.05).shuffled()
+r = orc.wcsph(2, c.params, c.arrays)
+np.savez_compressed(os.path.join(HERE, "wcsph2d_small.npz"), **r)
+print("golden vectors written")
