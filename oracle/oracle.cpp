@@ -197,8 +197,12 @@ int64_t pairs_cells(const Grid& g, int mode, double kfac, int64_t n, const R* x,
 // ----------------------------------------------------------------------------
 template <class R>
 inline R tait_eos(const WcsphParams& P, R rho) {
+    // (rho/rho0)^gamma - 1 evaluated as expm1(gamma * log1p((rho - rho0)/rho0)): the same function, but
+    // without the cancellation of pow(..) - 1 near rho0 (which costs ~2 digits per 1e-2 of compression and
+    // would make an f32 comparison at 1e-5 meaningless).
     const R B = (R)(P.rho0 * P.c0 * P.c0 / P.gamma);
-    return B * (std::pow(rho / (R)P.rho0, (R)P.gamma) - (R)1);
+    const R e = (rho - (R)P.rho0) / (R)P.rho0;
+    return B * std::expm1((R)P.gamma * std::log1p(e));
 }
 
 template <class R>

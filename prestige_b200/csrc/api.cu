@@ -174,6 +174,7 @@ void pst_destroy(pst_ctx* ctx) {
     cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
     cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->stage); cudaFree(ctx->d_flags);
     cudaFree(ctx->d_counters);
+    if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -394,6 +395,7 @@ pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value) {
     if (s == "n_ghost_l") { *value = (double)ctx->n_ghost_l; return PST_OK; }
     if (s == "n_ghost_r") { *value = (double)ctx->n_ghost_r; return PST_OK; }
     if (s == "ordered") { *value = ctx->ordered; return PST_OK; }
+    if (s == "particles_per_occupied_cell") { *value = pst_param(ctx, "_ppc", 0.0); return PST_OK; }
     if (s == "contacts_total") {  // sum of hist_n over owned particles
         PstArray* hn = pst_find(ctx, "hist_n");
         if (!hn) return pst_fail(ctx, PST_EINVAL, "no contact history in this context");

@@ -36,12 +36,19 @@ __global__ void __launch_bounds__(kThreads) k_keys(GridDev<R> g, int n, const R*
 }
 
 // start[k] = first sorted index whose key is >= k.  Thread s owns the keys in (key[s-1], key[s]].
+// Also counts the occupied cells (counters[2]) so the host can size pair-kernel tiles from the real
+// mean occupancy instead of a guess.
 __global__ void __launch_bounds__(kThreads) k_bounds(int n, uint32_t ncells, const uint32_t* __restrict__ keys,
-                                                     int32_t* __restrict__ cell_start) {
+                                                     int32_t* __restrict__ cell_start, unsigned long long* __restrict__ counters) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n) return;
-    const long long prev = s == 0 ? -1ll : (long long)keys[s - 1];
-    const long long cur = s == n ? (long long)ncells : (long long)keys[s];
+    const bool active = s <= n;
+    long long prev = 0, cur = -1;
+    if (active) {
+        prev = s == 0 ? -1ll : (long long)keys[s - 1];
+        cur = s == n ? (long long)ncells : (long long)keys[s];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active && s < n && cur != prev);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], (unsigned long long)__popc(m));
     for (long long k = prev + 1; k <= cur; ++k) cell_start[k] = s;
 }
 
@@ -182,6 +189,7 @@ pst_status pst_nnps_alloc(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 8 * sizeof(int32_t), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stats, cudaEventDisableTiming));
     ctx->sort_tmp_bytes = 0;
     PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, ctx->keys_in, ctx->keys_out, ctx->vals_in,
                                                   ctx->vals_out, (int)cap, 0, 32, ctx->stream));
@@ -206,7 +214,23 @@ pst_status pst_nnps_build(pst_ctx* ctx) {
                                                       n, 0, ctx->grid.key_bits, ctx->stream));
         ctx->launches += (ctx->grid.key_bits + 7) / 8 + 2;  // CUB onesweep: histogram + scan + one pass per 8 bits
     }
-    PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, ctx->grid.ncells, ctx->keys_out, ctx->cell_start);
+    // occupied-cell count of the PREVIOUS build (read back asynchronously; the very first build waits once)
+    if (ctx->stats_pending) {
+        PST_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
+        ctx->stats_pending = false;
+        if (ctx->h_counters[2] > 0) ctx->params["_ppc"] = (double)ctx->h_counters[3] / (double)ctx->h_counters[2];
+    }
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(unsigned long long), ctx->stream));
+    PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, ctx->grid.ncells, ctx->keys_out, ctx->cell_start, ctx->d_counters);
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaEventRecord(ctx->ev_stats, ctx->stream));
+    ctx->h_counters[3] = (unsigned long long)n;
+    ctx->stats_pending = true;
+    if (ctx->params.find("_ppc") == ctx->params.end()) {   // first build: one-time wait so the first force pass is tuned too
+        PST_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
+        ctx->stats_pending = false;
+        if (ctx->h_counters[2] > 0) ctx->params["_ppc"] = (double)n / (double)ctx->h_counters[2];
+    }
     if (n > 0) {
         PermuteList L;
         L.n8 = L.n4 = 0;

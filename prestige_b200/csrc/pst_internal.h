@@ -66,6 +66,8 @@ struct pst_ctx {
     bool nbrs_valid = false;
     bool eos_valid = false;
     uint64_t launches = 0;
+    cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)
+    bool stats_pending = false;
     PstComm* comm = nullptr;
     mutable std::string err;
 };
@@ -144,7 +146,7 @@ __device__ __forceinline__ R dist2(R dx, R dy, R dz) {
 template <class R>
 struct GridDev {
     R lo[3];
-    R inv_cell;
+    R inv_cell, cell;
     int n[3];
     int cx_lo, cx_hi;
     int bits;
@@ -221,7 +223,7 @@ template <class R>
 inline GridDev<R> make_grid_dev(const PstGrid& g) {
     GridDev<R> d;
     for (int a = 0; a < 3; ++a) { d.lo[a] = (R)g.lo[a]; d.n[a] = g.n[a]; }
-    d.inv_cell = (R)g.inv_cell;
+    d.inv_cell = (R)g.inv_cell; d.cell = (R)g.cell;
     d.cx_lo = g.cx_lo; d.cx_hi = g.cx_hi;
     d.bits = g.bits;
     return d;

@@ -40,7 +40,7 @@ WcsphConst<R> make_const(pst_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// EOS: p = B((rho/rho0)^gamma - 1), and p/rho^2 which is what the momentum body consumes.
+// EOS: p = B((rho/rho0)^gamma - 1) = B expm1(gamma log1p(rho/rho0 - 1)), and p/rho^2 which is what the momentum body consumes.
 // Runs over owned + ghost particles.
 // ---------------------------------------------------------------------------------------------
 template <class R>
@@ -49,11 +49,9 @@ __global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, co
     const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= hi) return;
     const R r = rho[s];
-    const R q = r / C.rho0;
-    R pw;
-    if (C.gamma_is_7) { const R q2 = q * q, q4 = q2 * q2; pw = q4 * q2 * q; }
-    else pw = pow(q, C.gamma);
-    const R pr = C.B * (pw - (R)1);
+    // (rho/rho0)^gamma - 1 without cancellation near rho0 (same form as the oracle)
+    const R e = (r - C.rho0) / C.rho0;
+    const R pr = C.B * expm1(C.gamma * log1p(e));
     p[s] = pr;
     por2[s] = pr / (r * r);
 }
@@ -80,11 +78,28 @@ __device__ __forceinline__ void load_i(IState<R, DIM>& I, const WcsphConst<R>& C
     I.rc2 = mul_rn(rc, rc);
 }
 
-// caller has already established 0 < r2 < rc2 with the exact test
+// 1/sqrt(x) and 1/x for normal positive x: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) + ONE cubically
+// convergent correction, no special-case branches.  Error ~2 ulp (e^3 ~ 2^-66 is below the rounding).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2
+    return fma(y, e * fma(0.375, e, 0.5), y);               // y (1 + e/2 + 3 e^2 / 8)
+}
+__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);                       // 1 - x y
+    return fma(y, fma(e, e, e), y);                         // y (1 + e + e^2)
+}
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+
+// caller has already established 0 < r2 < rc2 with the exact test.  Branch-free: one rsqrt, one rcp.
 template <class R, int DIM, bool CONT, bool MOM>
 __device__ __forceinline__ void pair_body(const WcsphConst<R>& C, const IState<R, DIM>& I, R dx, R dy, R dz, R r2, R uj, R vj, R wj,
                                           R rhoj, R mj, R por2j, Acc<R>& a) {
-    const R r = sqrt(r2);
+    const R r = r2 * fast_rsqrt(r2);
     const R t = (R)1 - r * I.half_inv_h;
     const R gf = I.gfc * (t * t * t);
     const R du = I.u - uj, dv = I.v - vj, dw = DIM == 3 ? I.w - wj : (R)0;
@@ -93,11 +108,12 @@ __device__ __forceinline__ void pair_body(const WcsphConst<R>& C, const IState<R
     const R mgf = mj * gf;
     if (CONT) a.arho += mgf * vx;
     if (MOM) {
-        R Pi = (R)0;
-        if (vx < (R)0) {
-            const R mu = I.h * vx / (r2 + I.eta2);
-            Pi = (C.beta * mu - C.alpha_c0) * mu / ((R)0.5 * (I.rho + rhoj));
-        }
+        // Pi = (beta mu - alpha c0) mu / rho_bar,  mu = h vx / (r2 + eta2),  rho_bar = (rho_i + rho_j)/2
+        const R rhos = I.rho + rhoj;
+        const R inv = fast_rcp((r2 + I.eta2) * rhos);
+        const R wv = I.h * vx * inv;                        // mu / (2 rho_bar)
+        const R mu = wv * rhos;
+        const R Pi = vx < (R)0 ? (C.beta * mu - C.alpha_c0) * (wv + wv) : (R)0;
         const R c = -mgf * (I.por2 + por2j + Pi);
         a.au += c * dx;
         a.av += c * dy;
@@ -322,6 +338,252 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// variant 2 (default): shared-memory tiles, ONE WARP PER CELL, candidate-parallel scan
+//
+//   * tile staging as in variant 1 (the (A+2)(B+2) candidate runs, coalesced, once per CTA);
+//   * a warp takes one cell at a time.  All particles of a cell share the same 9 (3) candidate runs,
+//     so the warp flattens them ONCE into a per-lane register cache: lane l holds candidates
+//     l, l+32, l+64, ... as f32 coordinates (tile-local for f64 contexts) plus their staged index;
+//   * per particle i (warp-uniform, broadcast from shared memory) the 32 lanes test 32 candidates
+//     per step -- no divergence, no shared-memory traffic -- and ballot-compact the hits into a
+//     per-warp queue;  f64 contexts use the f32 distance only as a CONSERVATIVE pre-filter
+//     (relative margin 2^-15 >> the 1.5e-6 worst-case f32 error for coordinates within 4 cells of
+//     the origin; cells holding farther particles switch the filter off), the exact FMA-free f64
+//     test runs on the survivors, so the neighbour set is still bit-exact;
+//   * the queue is drained 32 hits at a time: every lane evaluates the pair body for a different j
+//     of the SAME i, partial sums are combined with a 6-step transposing butterfly.
+// ---------------------------------------------------------------------------------------------
+// staging capacity of the warp-per-cell kernel: 113 KB per CTA (two CTAs per SM) minus 1 KB of tables minus the
+// per-warp queue and slot->index tables (2 x 512 x u16 each)
+template <class R, int NT>
+__host__ __device__ constexpr int kCellwarpJcap() { return (int)((113 * 1024 - 1024 - (NT / 32) * 512 * 4) / (9 * sizeof(R))) & ~1; }
+
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
+__global__ void __launch_bounds__(NT, 384 / NT) k_wcsph_cellwarp(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
+    using D = TileDims<DIM, TA, TB>;
+    constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
+    constexpr int NW = NT / 32, MAXT = 16, QCAP = 32 * MAXT;
+    constexpr int NRUN = DIM == 3 ? 9 : 3;
+    constexpr bool LOCAL = sizeof(R) == 8;       // f64: f32 pre-filter in local coordinates
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = T.G, W = G + 3;
+    int* s_cs = reinterpret_cast<int*>(smem_raw);            // NR * W   virtual cell boundaries
+    int* s_gbeg = s_cs + NR * W;                              // NR
+    int* s_voff = s_gbeg + NR;                                // NR + 1
+    int* s_next = s_voff + NR + 1;                            // 1        next cell to hand out
+    size_t off = ((size_t)(NR * W + NR + NR + 1 + 1) * sizeof(int) + 15) & ~(size_t)15;
+    unsigned short* s_q = reinterpret_cast<unsigned short*>(smem_raw + off);   // NW * QCAP
+    off += (size_t)NW * QCAP * sizeof(unsigned short);
+    unsigned short* s_jid = reinterpret_cast<unsigned short*>(smem_raw + off);   // NW * QCAP: staged index of cached candidate (t, lane)
+    off += (size_t)NW * QCAP * sizeof(unsigned short);
+    R* s_x = reinterpret_cast<R*>(smem_raw + off);
+    constexpr int JC = kCellwarpJcap<R, NT>();   // compile-time, so the 9 staged arrays are one base + immediates
+    R* s_y = s_x + JC; R* s_z = s_y + JC; R* s_u = s_z + JC; R* s_v = s_u + JC; R* s_w = s_v + JC;
+    R* s_rho = s_w + JC; R* s_m = s_rho + JC; R* s_por2 = s_m + JC;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tf = b % T.tiles[2]; b /= T.tiles[2];
+    const int ty = DIM == 3 ? b % T.tiles[1] : 0; if (DIM == 3) b /= T.tiles[1];
+    const int tx = b;
+    const int cx0 = tx * TA, cy0 = ty * BB, f0 = tf * G;
+    const int nf = DIM == 3 ? g.n[2] : g.n[1];
+    const int ncx = g.n[0], ncy = DIM == 3 ? g.n[1] : 1;
+
+    for (int t = tid; t < NR * W; t += NT) {
+        const int q = t / W, tt = t - q * W;
+        const int rx = q / RY, ry = q - rx * RY;
+        const int cx = cx0 - 1 + rx, cy = DIM == 3 ? cy0 - 1 + ry : 0;
+        int gi = 0;
+        if (cx >= 0 && cx < ncx && cy >= 0 && cy < ncy) {
+            const int col = DIM == 3 ? cx * ncy + cy : cx;
+            gi = A.cell_start[(size_t)col * nf + min(max(f0 - 1 + tt, 0), nf)];
+        }
+        s_cs[t] = gi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int q = 0; q < NR; ++q) {
+            s_gbeg[q] = s_cs[q * W];
+            s_voff[q] = acc;
+            acc += s_cs[q * W + W - 1] - s_cs[q * W];
+        }
+        s_voff[NR] = acc;
+        *s_next = NW;
+    }
+    __syncthreads();
+    // number of i particles in the tile (sum over the centre runs, cells f0 .. f0+G-1)
+    int ni = 0;
+    for (int c = 0; c < NI; ++c) {
+        const int lx = c / BB, ly = c - lx * BB;
+        const int q = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
+        if (cx0 + lx >= g.cx_lo && cx0 + lx <= g.cx_hi && cy0 + ly < ncy) ni += s_cs[q * W + G + 1] - s_cs[q * W + 1];
+    }
+    if (ni == 0) return;
+    const int M = s_voff[NR];
+    if (M > JC) {   // tile denser than the staging buffer: exact per-particle gather for its particles
+        for (int c = 0; c < NI; ++c) {
+            const int lx = c / BB, ly = c - lx * BB;
+            const int q = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
+            if (!(cx0 + lx >= g.cx_lo && cx0 + lx <= g.cx_hi && cy0 + ly < ncy)) continue;
+            for (int s = s_cs[q * W + 1] + tid; s < s_cs[q * W + G + 1]; s += NT) gather_one<R, DIM, false, CONT, MOM>(g, C, A, s);
+        }
+        return;
+    }
+    __syncthreads();   // everyone has read the global-index form of s_cs
+    for (int t = tid; t < NR * W; t += NT) {
+        const int q = t / W;
+        s_cs[t] = s_voff[q] + (s_cs[t] - s_gbeg[q]);
+    }
+    for (int v = tid; v < M; v += NT) {
+        int q = 0;
+        while (q + 1 < NR && v >= s_voff[q + 1]) ++q;
+        const int gj = s_gbeg[q] + (v - s_voff[q]);
+        s_x[v] = A.x[gj]; s_y[v] = A.y[gj]; if (DIM == 3) s_z[v] = A.z[gj];
+        s_u[v] = A.u[gj]; s_v[v] = A.v[gj]; if (DIM == 3) s_w[v] = A.w[gj];
+        s_rho[v] = A.rho[gj]; s_m[v] = A.m[gj]; s_por2[v] = A.por2[gj];
+    }
+    __syncthreads();
+
+    unsigned short* q_w = s_q + warp * QCAP;
+    unsigned short* jid_w = s_jid + warp * QCAP;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float far_lim = 4.0f * (float)g.cell;
+    // result routing after the butterfly: lane 0 au, 8 av, 16 aw, 24 arho
+    R* const out_ptr = lane < 8 ? A.au : lane < 16 ? A.av : lane < 24 ? A.aw : A.arho;
+    const R out_g = lane < 8 ? C.g[0] : lane < 16 ? C.g[1] : lane < 24 ? C.g[2] : (R)0;
+    const bool out_lane = (lane & 7) == 0 && (lane < 24 ? (MOM && (DIM == 3 || lane < 16)) : CONT);
+    IState<R, DIM> I;
+    I.h = (R)-1;
+    for (int c = warp;;) {     // cells of the tile, handed out dynamically (warp-uniform)
+        if (c >= NI * G) break;
+        const int col = c / G, lf = c - col * G;
+        const int lx = col / BB, ly = col - lx * BB;
+        const int q0 = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
+        int ib = 0, ie = 0;
+        if (cx0 + lx >= g.cx_lo && cx0 + lx <= g.cx_hi && cy0 + ly < ncy && f0 + lf < nf) { ib = s_cs[q0 * W + lf + 1]; ie = s_cs[q0 * W + lf + 2]; }
+        if (ib < ie) {
+            // the cell's candidate runs, flattened
+            int rb[NRUN], rp[NRUN + 1];
+            rp[0] = 0;
+#pragma unroll
+            for (int k = 0; k < NRUN; ++k) {
+                const int ax = DIM == 3 ? k / 3 : k, ay = DIM == 3 ? k - ax * 3 : 0;
+                const int q = (lx + ax) * RY + (DIM == 3 ? ly + ay : 0);
+                rb[k] = s_cs[q * W + lf];
+                rp[k + 1] = rp[k] + (s_cs[q * W + lf + 3] - rb[k]);
+            }
+            const int total = rp[NRUN];
+            const int gi0 = s_gbeg[q0] - s_voff[q0];
+            const R ox = LOCAL ? s_x[ib] : (R)0, oy = LOCAL ? s_y[ib] : (R)0, oz = (LOCAL && DIM == 3) ? s_z[ib] : (R)0;
+            for (int cbase = 0; cbase < total; cbase += 32 * MAXT) {
+                // ---- per-lane register cache of this chunk's candidates (f32; tile-local for f64 contexts)
+                float jx[MAXT], jy[MAXT], jz[MAXT];
+                bool far = false;
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < MAXT; ++t) {
+                    const int v = cbase + t * 32 + lane;
+                    int jv = -1;
+                    if (v < total) {
+#pragma unroll
+                        for (int k = 0; k < NRUN; ++k)
+                            if (v >= rp[k] && v < rp[k + 1]) jv = rb[k] + (v - rp[k]);
+                    }
+                    jid_w[t * 32 + lane] = (unsigned short)jv;
+                    if (jv >= 0) {
+                        jx[t] = (float)(s_x[jv] - ox); jy[t] = (float)(s_y[jv] - oy); jz[t] = DIM == 3 ? (float)(s_z[jv] - oz) : 0.0f;
+                        if (LOCAL) far |= fabsf(jx[t]) > far_lim || fabsf(jy[t]) > far_lim || fabsf(jz[t]) > far_lim;
+                    } else {
+                        jx[t] = jy[t] = jz[t] = __int_as_float(0x7fc00000);   // NaN: never a hit, whatever the cutoff
+                    }
+                }
+                if (LOCAL) far = __any_sync(0xffffffffu, far);
+                __syncwarp();
+                const int nt = min(MAXT, (total - cbase + 31) >> 5);
+                const bool first = cbase == 0;
+                R h_next = A.h[gi0 + ib];
+                for (int iv = ib; iv < ie; ++iv) {    // warp-uniform: one particle i at a time
+                    const int gi = gi0 + iv;
+                    const R hi = h_next;
+                    if (iv + 1 < ie) h_next = A.h[gi + 1];           // prefetch: keeps the global-load latency off the chain
+                    if (hi != I.h) load_i<R, DIM>(I, C, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, hi);   // h-derived constants
+                    I.x = s_x[iv]; I.y = s_y[iv]; I.z = DIM == 3 ? s_z[iv] : (R)0;
+                    const float xf = (float)(I.x - ox), yf = (float)(I.y - oy), zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
+                    float rc2f;
+                    if (LOCAL) rc2f = far ? __int_as_float(0x7f800000) : __double2float_ru((double)I.rc2 * (1.0 + 1.0 / 32768.0));
+                    else rc2f = (float)I.rc2;
+                    // ---- phase 1: 32 candidates per step, ballot-compacted (slot numbers) into the warp's queue.
+                    // Groups of 4 steps are branch-free so their arithmetic overlaps; padding slots hold NaN.
+                    int tail = 0;
+#pragma unroll
+                    for (int t0 = 0; t0 < MAXT; t0 += 4) {
+                        if (t0 < nt) {
+                            unsigned m[4];
+                            bool hit[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int t = t0 + k;
+                                const float dxf = xf - jx[t], dyf = yf - jy[t], dzf = zf - jz[t];
+                                float r2f;
+                                if (LOCAL) { r2f = dxf * dxf + dyf * dyf; if (DIM == 3) r2f += dzf * dzf; }
+                                else r2f = dist2<DIM, float>(dxf, dyf, dzf);
+                                hit[k] = LOCAL ? (r2f <= rc2f) : (r2f < rc2f && r2f > 0.0f);
+                                m[k] = __ballot_sync(0xffffffffu, hit[k]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (hit[k]) q_w[tail + __popc(m[k] & lt_mask)] = (unsigned short)((t0 + k) * 32 + lane);
+                                tail += __popc(m[k]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // ---- phase 2: the pair body, TWO hits per lane per pass (independent chains -> ILP), branch-free:
+                    // an empty slot evaluates a harmless dummy pair (r2 = 1, m_j = 0).
+                    I.u = s_u[iv]; I.v = s_v[iv]; I.w = DIM == 3 ? s_w[iv] : (R)0;
+                    I.rho = s_rho[iv]; I.por2 = s_por2[iv];
+                    Acc<R> a{0, 0, 0, 0}, a2{0, 0, 0, 0};
+                    for (int head = 0; head < tail; head += 64) {
+                        const bool v0 = head + lane < tail, v1 = head + 32 + lane < tail;
+                        const int j0 = v0 ? jid_w[q_w[head + lane]] : iv;
+                        const int j1 = v1 ? jid_w[q_w[head + 32 + lane]] : iv;
+                        const R dx0 = I.x - s_x[j0], dy0 = I.y - s_y[j0], dz0 = DIM == 3 ? I.z - s_z[j0] : (R)0;
+                        const R dx1 = I.x - s_x[j1], dy1 = I.y - s_y[j1], dz1 = DIM == 3 ? I.z - s_z[j1] : (R)0;
+                        R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
+                        const bool in0 = v0 && r20 < I.rc2 && r20 > (R)0;     // the exact test (the set is defined here)
+                        const bool in1 = v1 && r21 < I.rc2 && r21 > (R)0;
+                        r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
+                        const R m0 = in0 ? s_m[j0] : (R)0, m1 = in1 ? s_m[j1] : (R)0;
+                        pair_body<R, DIM, CONT, MOM>(C, I, dx0, dy0, dz0, r20, s_u[j0], s_v[j0], DIM == 3 ? s_w[j0] : (R)0, s_rho[j0], m0, s_por2[j0], a);
+                        pair_body<R, DIM, CONT, MOM>(C, I, dx1, dy1, dz1, r21, s_u[j1], s_v[j1], DIM == 3 ? s_w[j1] : (R)0, s_rho[j1], m1, s_por2[j1], a2);
+                    }
+                    a.au += a2.au; a.av += a2.av; a.aw += a2.aw; a.arho += a2.arho;
+                    __syncwarp();
+                    // ---- combine the 32 partial sums: transposing butterfly, 6 shuffles for 4 values
+                    const bool b4 = lane & 16, b3 = lane & 8;
+                    const R s0 = b4 ? a.au : a.aw, s1 = b4 ? a.av : a.arho;
+                    R k0 = b4 ? a.aw : a.au, k1 = b4 ? a.arho : a.av;
+                    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    const R sx = b3 ? k0 : k1;
+                    R k = b3 ? k1 : k0;
+                    k += __shfl_xor_sync(0xffffffffu, sx, 8);
+                    k += __shfl_xor_sync(0xffffffffu, k, 4);
+                    k += __shfl_xor_sync(0xffffffffu, k, 2);
+                    k += __shfl_xor_sync(0xffffffffu, k, 1);
+                    if (out_lane) out_ptr[gi] = first ? k + out_g : out_ptr[gi] + k;
+                }
+            }
+        }
+        int nc = 0;
+        if (lane == 0) nc = atomicAdd(s_next, 1);
+        c = __shfl_sync(0xffffffffu, nc, 0);
+    }
+}
+
 template <class R>
 ForceArgs<R> make_args(pst_ctx* ctx) {
     ForceArgs<R> A;
@@ -346,9 +608,9 @@ pst_status launch_gather(pst_ctx* ctx, bool cont, bool mom) {
     return PST_OK;
 }
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
+template <class R, int DIM, int TA, int TB, int NT, int VARIANT, bool CONT, bool MOM>
 pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
-    auto kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM>;
+    auto kern = VARIANT == 1 ? k_wcsph_cellwarp<R, DIM, TA, TB, NT, CONT, MOM> : k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -359,41 +621,55 @@ pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
     return PST_OK;
 }
 
-template <class R, int DIM>
+// VARIANT 1: warp-per-cell (2 CTAs/SM, no per-thread lists); VARIANT 2: per-thread hit lists (1 CTA/SM)
+template <class R, int DIM, int VARIANT>
 pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
-    constexpr int TA = 2, TB = 2, NT = 256;
+    constexpr int TA = 2, TB = 2, NT = VARIANT == 1 ? 192 : 256;
     using D = TileDims<DIM, TA, TB>;
     const PstGrid& g = ctx->grid;
     const int nf = DIM == 3 ? g.n[2] : g.n[1];
-    // tile depth along the fast axis: fill NT threads at the mean occupancy of the occupied cells
-    double ppc = pst_param(ctx, "_ppc", 0.0);
+    double ppc = pst_param(ctx, "_ppc", 0.0);      // mean occupancy of the occupied cells (measured by k_bounds)
     if (!(ppc > 0)) ppc = DIM == 3 ? 14.0 : 6.0;
-    const int user_G = pst_option(ctx, "tile_g", 0);
-    int G = user_G > 0 ? user_G : (int)std::max(1.0, std::floor(0.95 * NT / (D::NI * ppc)));
-    G = std::min(G, std::max(1, nf));
+    const size_t budget = (size_t)pst_option(ctx, "tile_smem_kb", VARIANT == 1 ? 113 : 200) * 1024;
     TileShape T;
+    T.lcap = pst_option(ctx, "tile_lcap", DIM == 3 ? 80 : 32);
+    const size_t fixed = VARIANT == 1 ? (size_t)(NT / 32) * 512 * sizeof(unsigned short) * 2 : (size_t)T.lcap * NT * sizeof(unsigned short);
+    const int user_G = pst_option(ctx, "tile_g", 0);
+    int G = user_G;
+    if (G <= 0) {
+        if (VARIANT == 1) {   // deepest tile whose staged runs fit the buffer with 12 % headroom
+            const double jc = (double)kCellwarpJcap<R, NT>();
+            G = (int)std::floor(jc / (1.12 * D::NR * ppc)) - 2;
+        } else {              // one thread per particle
+            G = (int)std::floor(0.95 * NT / (D::NI * ppc));
+        }
+    }
+    G = std::min(std::max(G, 1), std::max(1, nf));
     T.G = G;
     T.tiles[0] = (g.n[0] + TA - 1) / TA;
     T.tiles[1] = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
     T.tiles[2] = (nf + G - 1) / G;
-    T.lcap = pst_option(ctx, "tile_lcap", DIM == 3 ? 80 : 32);
     const size_t ints = ((size_t)(D::NR * (G + 3) + D::NR + D::NR + 1 + D::NI + D::NI + 1) * sizeof(int) + 15) & ~(size_t)15;
-    const size_t list = (size_t)T.lcap * NT * sizeof(unsigned short);
-    const size_t budget = (size_t)pst_option(ctx, "tile_smem_kb", 200) * 1024;
-    if (ints + list + 9 * sizeof(R) * 64 > budget) return pst_fail(ctx, PST_EINVAL, "tile_smem_kb too small");
-    int jcap = (int)((budget - ints - list) / (9 * sizeof(R)));
-    jcap = std::min(jcap, 65535) & ~1;   // hit lists hold 16-bit staged indices
+    if (ints + fixed + 9 * sizeof(R) * 64 > budget) return pst_fail(ctx, PST_EINVAL, "tile_smem_kb too small");
+    int jcap = (int)((budget - ints - fixed) / (9 * sizeof(R)));
+    jcap = std::min(jcap, 65535) & ~1;   // hit lists / queues hold 16-bit staged indices
+    size_t smem = ints + (size_t)jcap * 9 * sizeof(R) + fixed;
+    if (VARIANT == 1) {
+        if (ints > 1024) return pst_fail(ctx, PST_EINVAL, "tile_g too large for the warp-per-cell kernel");
+        jcap = kCellwarpJcap<R, NT>();
+        smem = 113 * 1024;
+    }
     T.jcap = jcap;
-    const size_t smem = ints + (size_t)jcap * 9 * sizeof(R) + list;
-    if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, true, true>(ctx, T, smem);
-    if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, true, false>(ctx, T, smem);
-    return launch_tiled_k<R, DIM, TA, TB, NT, false, true>(ctx, T, smem);
+    if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, true>(ctx, T, smem);
+    if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, false>(ctx, T, smem);
+    return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, false, true>(ctx, T, smem);
 }
 
 template <class R, int DIM, bool MORTON>
 pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
     const int variant = pst_option(ctx, "force_kernel", 1);
-    if (variant == 1 && !MORTON) return launch_tiled<R, DIM>(ctx, cont, mom);
+    if (variant == 1 && !MORTON) return launch_tiled<R, DIM, 1>(ctx, cont, mom);
+    if (variant == 2 && !MORTON) return launch_tiled<R, DIM, 2>(ctx, cont, mom);
     return launch_gather<R, DIM, MORTON>(ctx, cont, mom);
 }
 

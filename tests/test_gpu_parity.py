@@ -297,8 +297,9 @@ def test_dem_antisymmetry_bit_exact():
     """F_ji = -F_ij bit for bit: the summed force of an isolated pair is exactly zero."""
     R = 1e-3
     a = {k: np.zeros(2) for k in ("y", "z", "u", "v", "w", "wx", "wy", "wz")}
-    a["x"] = np.array([0.0101, 0.0101 + 1.9 * R]); a["y"] += 0.0103; a["z"] += 0.0107
-    a["u"] = np.array([0.3, -0.2]); a["v"] = np.array([0.01, 0.4]); a["wx"] = np.array([30.0, -7.0]); a["wz"] = np.array([3.0, 11.0])
+    a["x"] = np.array([0.0101, 0.0101 + 1.5 * R]); a["y"] = np.array([0.0103, 0.0103 + 0.9 * R]); a["z"] = np.array([0.0107, 0.0107 - 0.7 * R])
+    a["u"] = np.array([0.3, -0.2]); a["v"] = np.array([0.01, 0.4]); a["w"] = np.array([-0.15, 0.05])
+    a["wx"] = np.array([30.0, -7.0]); a["wy"] = np.array([-12.0, 5.0]); a["wz"] = np.array([3.0, 11.0])
     a["rad"] = np.full(2, R); a["m"] = np.full(2, 1e-5); a["inertia"] = np.full(2, 4e-12); a["tag"] = np.zeros(2, np.int32)
     blk = synth.Block("pair", 3, "dem", a, synth.dem_params(R), (0, 0, 0), (0.03, 0.03, 0.03), 2 * R * synth.CELL_MARGIN, max_contacts=4)
     with _ctx(blk, np.float64) as ctx:
