@@ -250,6 +250,8 @@ def main():
         run_reference(args, rank)
         return
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     import prestige_b200 as pb
@@ -382,7 +384,7 @@ def main():
             b_step, b_force = B_ALG[key], B_FORCE[key]
         n_local = n
         ach = b_force * n_local / t_force / 1e9
-        kern = ("k_wcsph_tiled" if args.force_kernel == 1 and args.key == "linear" else "k_wcsph_gather") if block.physics == "wcsph" else "k_dem_forces"
+        kern = ({1: "k_wcsph_cellwarp", 2: "k_wcsph_tiled"}.get(args.force_kernel, "k_wcsph_gather") if args.key == "linear" else "k_wcsph_gather") if block.physics == "wcsph" else "k_dem_forces"
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):

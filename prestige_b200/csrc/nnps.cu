@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(kThreads) k_bounds(int n, uint32_t ncells, con
         prev = s == 0 ? -1ll : (long long)keys[s - 1];
         cur = s == n ? (long long)ncells : (long long)keys[s];
     }
-    const unsigned m = __ballot_sync(0xffffffffu, active && s < n && cur != prev);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], (unsigned long long)__popc(m));
+    const int occupied = __syncthreads_count(active && s < n && cur != prev);   // one atomic per block, not per warp
+    if (threadIdx.x == 0 && occupied) atomicAdd(&counters[2], (unsigned long long)occupied);
     for (long long k = prev + 1; k <= cur; ++k) cell_start[k] = s;
 }
 

@@ -354,6 +354,30 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
 //   * the queue is drained 32 hits at a time: every lane evaluates the pair body for a different j
 //     of the SAME i, partial sums are combined with a 6-step transposing butterfly.
 // ---------------------------------------------------------------------------------------------
+// phase 1 of the warp-per-cell kernel: NS steps of 32 candidates each, straight-line.
+template <int DIM, bool LOCAL, int NS>
+__device__ __forceinline__ int scan_steps(const float (&jx)[16], const float (&jy)[16], const float (&jz)[16], float xf, float yf, float zf,
+                                          float rc2f, unsigned lt_mask, int lane, unsigned short* __restrict__ q_w) {
+    unsigned m[NS];
+    bool hit[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const float dxf = xf - jx[t], dyf = yf - jy[t], dzf = zf - jz[t];
+        float r2f;
+        if (LOCAL) { r2f = dxf * dxf + dyf * dyf; if (DIM == 3) r2f += dzf * dzf; }
+        else r2f = dist2<DIM, float>(dxf, dyf, dzf);
+        hit[t] = LOCAL ? (r2f <= rc2f) : (r2f < rc2f && r2f > 0.0f);
+        m[t] = __ballot_sync(0xffffffffu, hit[t]);
+    }
+    int tail = 0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        if (hit[t]) q_w[tail + __popc(m[t] & lt_mask)] = (unsigned short)(t * 32 + lane);
+        tail += __popc(m[t]);
+    }
+    return tail;
+}
+
 // staging capacity of the warp-per-cell kernel: 113 KB per CTA (two CTAs per SM) minus 1 KB of tables minus the
 // per-warp queue and slot->index tables (2 x 512 x u16 each)
 template <class R, int NT>
@@ -457,6 +481,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) k_wcsph_cellwarp(GridDev<R> g, W
     const bool out_lane = (lane & 7) == 0 && (lane < 24 ? (MOM && (DIM == 3 || lane < 16)) : CONT);
     IState<R, DIM> I;
     I.h = (R)-1;
+    float rc2f_h = 0.0f;
     for (int c = warp;;) {     // cells of the tile, handed out dynamically (warp-uniform)
         if (c >= NI * G) break;
         const int col = c / G, lf = c - col * G;
@@ -509,36 +534,21 @@ __global__ void __launch_bounds__(NT, 384 / NT) k_wcsph_cellwarp(GridDev<R> g, W
                     const int gi = gi0 + iv;
                     const R hi = h_next;
                     if (iv + 1 < ie) h_next = A.h[gi + 1];           // prefetch: keeps the global-load latency off the chain
-                    if (hi != I.h) load_i<R, DIM>(I, C, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, hi);   // h-derived constants
+                    if (hi != I.h) {    // h-derived constants (uniform h: computed once per warp)
+                        load_i<R, DIM>(I, C, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, hi);
+                        rc2f_h = LOCAL ? __double2float_ru((double)I.rc2 * (1.0 + 1.0 / 32768.0)) : (float)I.rc2;
+                    }
+                    const float rc2f = (LOCAL && far) ? __int_as_float(0x7f800000) : rc2f_h;
                     I.x = s_x[iv]; I.y = s_y[iv]; I.z = DIM == 3 ? s_z[iv] : (R)0;
                     const float xf = (float)(I.x - ox), yf = (float)(I.y - oy), zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
-                    float rc2f;
-                    if (LOCAL) rc2f = far ? __int_as_float(0x7f800000) : __double2float_ru((double)I.rc2 * (1.0 + 1.0 / 32768.0));
-                    else rc2f = (float)I.rc2;
                     // ---- phase 1: 32 candidates per step, ballot-compacted (slot numbers) into the warp's queue.
-                    // Groups of 4 steps are branch-free so their arithmetic overlaps; padding slots hold NaN.
-                    int tail = 0;
-#pragma unroll
-                    for (int t0 = 0; t0 < MAXT; t0 += 4) {
-                        if (t0 < nt) {
-                            unsigned m[4];
-                            bool hit[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int t = t0 + k;
-                                const float dxf = xf - jx[t], dyf = yf - jy[t], dzf = zf - jz[t];
-                                float r2f;
-                                if (LOCAL) { r2f = dxf * dxf + dyf * dyf; if (DIM == 3) r2f += dzf * dzf; }
-                                else r2f = dist2<DIM, float>(dxf, dyf, dzf);
-                                hit[k] = LOCAL ? (r2f <= rc2f) : (r2f < rc2f && r2f > 0.0f);
-                                m[k] = __ballot_sync(0xffffffffu, hit[k]);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (hit[k]) q_w[tail + __popc(m[k] & lt_mask)] = (unsigned short)((t0 + k) * 32 + lane);
-                                tail += __popc(m[k]);
-                            }
-                        }
+                    // One straight-line block per group count, so all its steps overlap; padding slots hold NaN.
+                    int tail;
+                    switch ((nt + 3) >> 2) {
+                        case 1: tail = scan_steps<DIM, LOCAL, 4>(jx, jy, jz, xf, yf, zf, rc2f, lt_mask, lane, q_w); break;
+                        case 2: tail = scan_steps<DIM, LOCAL, 8>(jx, jy, jz, xf, yf, zf, rc2f, lt_mask, lane, q_w); break;
+                        case 3: tail = scan_steps<DIM, LOCAL, 12>(jx, jy, jz, xf, yf, zf, rc2f, lt_mask, lane, q_w); break;
+                        default: tail = scan_steps<DIM, LOCAL, 16>(jx, jy, jz, xf, yf, zf, rc2f, lt_mask, lane, q_w); break;
                     }
                     __syncwarp();
                     // ---- phase 2: the pair body, TWO hits per lane per pass (independent chains -> ILP), branch-free:
@@ -645,6 +655,7 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
         }
     }
     G = std::min(std::max(G, 1), std::max(1, nf));
+    if (VARIANT == 1) G = std::min(G, (256 - 2 * D::NR - 2 * D::NI - 3) / D::NR - 3);   // boundary tables must fit their 1 KB
     T.G = G;
     T.tiles[0] = (g.n[0] + TA - 1) / TA;
     T.tiles[1] = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;

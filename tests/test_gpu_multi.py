@@ -1,0 +1,44 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices): slab decomposition + NCCL send/recv halo through the C ABI."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_exchange_matches_single_domain(world, tmp_path):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    tot = 0
+    for rank in range(world):
+        d = json.load(open(tmp_path / f"rank{rank}.json"))
+        tot += d["n"]
+        for variant, errs in d["err"].items():
+            gl, gr = errs.pop("ghosts")
+            assert (gl > 0) == (rank > 0) and (gr > 0) == (rank < world - 1)
+            for k, e in errs.items():
+                assert e <= 1e-10, f"rank {rank} kernel variant {variant} {k}: {e:.3e}"
+    assert tot == d["n_whole"]
