@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wcsph3d_10m")
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--force-kernel", type=int, default=1)
+    ap.add_argument("--force-kernel", type=int, default=2)
     ap.add_argument("--key", default="linear", choices=["linear", "morton"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

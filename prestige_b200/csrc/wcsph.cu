@@ -169,7 +169,16 @@ __global__ void __launch_bounds__(kThreads) k_wcsph_gather(GridDev<R> g, WcsphCo
 }
 
 // ---------------------------------------------------------------------------------------------
-// variant 1: shared-memory tiles + per-thread hit lists
+// variant 2: shared-memory tiles, ONE THREAD PER PARTICLE, private hit lists
+//
+//   * staged per tile: only a float4 per candidate -- f32 coordinates (tile-local for f64 contexts) and, in .w,
+//     the candidate's global index.  16 B instead of 72 B per candidate leaves room for two CTAs per SM;
+//   * phase 1: each thread scans its 9 (3) runs with one LDS.128 and ~7 FP32 instructions per candidate
+//     (4 candidates in flight), appending hits to its private 16-bit list.  For f64 contexts this is a
+//     CONSERVATIVE pre-filter (margin 2^-15, switched off for tiles holding far-away particles);
+//   * phase 2: two hits per trip; the f64 state of j is gathered straight from global memory -- L1/L2 hits, since
+//     the CTA's threads share the same ~1300 candidates and staging has just touched them -- the exact
+//     FMA-free cutoff test decides membership, then the branch-free pair body runs.
 // ---------------------------------------------------------------------------------------------
 struct TileShape {
     int G;          // cells per tile along the fast axis
@@ -186,10 +195,14 @@ struct TileDims {
     static constexpr int RY = DIM == 3 ? BB + 2 : 1;               // runs along y
 };
 
+constexpr int kListsJcap = 2048;   // float4 slots staged per tile (32 KB)
+
 template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
-__global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
+__global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
     using D = TileDims<DIM, TA, TB>;
     constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
+    constexpr bool LOCAL = sizeof(R) == 8;
+    constexpr int JC = kListsJcap;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = T.G, W = G + 3;  // W boundaries per run
     // ---- shared memory carve-up
@@ -199,11 +212,10 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
     int* s_ibeg = s_voff + NR + 1;                            // NI       global begin of each i segment
     int* s_ipre = s_ibeg + NI;                                // NI + 1   prefix of i counts
     size_t off = ((size_t)(NR * W + NR + NR + 1 + NI + NI + 1) * sizeof(int) + 15) & ~(size_t)15;
-    R* s_x = reinterpret_cast<R*>(smem_raw + off);
-    const int JC = T.jcap;
-    R* s_y = s_x + JC; R* s_z = s_y + JC; R* s_u = s_z + JC; R* s_v = s_u + JC; R* s_w = s_v + JC;
-    R* s_rho = s_w + JC; R* s_m = s_rho + JC; R* s_por2 = s_m + JC;
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_por2 + JC);   // lcap * NT
+    double* s_org = reinterpret_cast<double*>(smem_raw + off);   // 3 (+1 pad): tile origin
+    off += 4 * sizeof(double);
+    float4* s_p4 = reinterpret_cast<float4*>(smem_raw + off);
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_p4 + JC);   // lcap * NT
 
     const int tid = threadIdx.x;
     // ---- which tile
@@ -220,13 +232,10 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
         const int q = t / W, tt = t - q * W;
         const int rx = q / RY, ry = q - rx * RY;
         const int cx = cx0 - 1 + rx, cy = DIM == 3 ? cy0 - 1 + ry : 0;
-        int gi = 0;
+        int gi = 0;   // column outside the grid: all boundaries equal -> empty run
         if (cx >= 0 && cx < ncx && cy >= 0 && cy < ncy) {
             const int col = DIM == 3 ? cx * ncy + cy : cx;
-            const int f = min(max(f0 - 1 + tt, 0), nf);
-            gi = A.cell_start[(size_t)col * nf + f];
-        } else {
-            gi = 0;  // column outside the grid: all boundaries equal -> empty run
+            gi = A.cell_start[(size_t)col * nf + min(max(f0 - 1 + tt, 0), nf)];
         }
         s_cs[t] = gi;
     }
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
         }
         s_voff[NR] = acc;
         // i segments: tile columns, fast cells [f0, f0 + G)  == boundaries tt = 1 .. G+1 of the centre runs
-        int ia = 0;
+        int ia = 0, first = -1;
         for (int c = 0; c < NI; ++c) {
             const int lx = c / BB, ly = c - lx * BB;
             const int q = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
@@ -250,14 +259,17 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
             s_ibeg[c] = beg;
             s_ipre[c] = ia;
             ia += cnt;
+            if (cnt > 0 && first < 0) first = beg;
         }
         s_ipre[NI] = ia;
+        if (LOCAL && first >= 0) { s_org[0] = (double)A.x[first]; s_org[1] = (double)A.y[first]; s_org[2] = DIM == 3 ? (double)A.z[first] : 0.0; }
+        else { s_org[0] = s_org[1] = s_org[2] = 0.0; }
     }
     __syncthreads();
     const int ni = s_ipre[NI];
     if (ni == 0) return;                      // empty tile (uniform exit)
     const int M = s_voff[NR];
-    if (M > JC) {
+    if (M > min(JC, T.jcap)) {
         // tile denser than the staging buffer: exact per-particle gather for its particles
         for (int ii = tid; ii < ni; ii += NT) {
             int c = 0;
@@ -272,15 +284,20 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
         s_cs[t] = s_voff[q] + (s_cs[t] - s_gbeg[q]);
     }
     // ---- stage candidates: flattened over the concatenated runs, coalesced inside each run
+    const R ox = (R)s_org[0], oy = (R)s_org[1], oz = (R)s_org[2];
+    const float far_lim = (float)(G + 6) * (float)g.cell;
+    bool far = false;
     for (int v = tid; v < M; v += NT) {
         int q = 0;
         while (q + 1 < NR && v >= s_voff[q + 1]) ++q;
         const int gj = s_gbeg[q] + (v - s_voff[q]);
-        s_x[v] = A.x[gj]; s_y[v] = A.y[gj]; if (DIM == 3) s_z[v] = A.z[gj];
-        s_u[v] = A.u[gj]; s_v[v] = A.v[gj]; if (DIM == 3) s_w[v] = A.w[gj];
-        s_rho[v] = A.rho[gj]; s_m[v] = A.m[gj]; s_por2[v] = A.por2[gj];
+        float4 p;
+        p.x = (float)(A.x[gj] - ox); p.y = (float)(A.y[gj] - oy); p.z = DIM == 3 ? (float)(A.z[gj] - oz) : 0.0f;
+        p.w = __int_as_float(gj);
+        if (LOCAL) far |= fabsf(p.x) > far_lim || fabsf(p.y) > far_lim || fabsf(p.z) > far_lim;
+        s_p4[v] = p;
     }
-    __syncthreads();
+    far = __syncthreads_or(far);
 
     const int LC = T.lcap;
     for (int ii0 = 0; ii0 < ni; ii0 += NT) {   // uniform trip count: rounds of NT particles
@@ -288,7 +305,8 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
         const bool active = ii < ni;
         int c = 0, gi = 0, lx = 0, ly = 0, lf = 0;
         IState<R, DIM> I;
-        Acc<R> a{0, 0, 0, 0};
+        Acc<R> a{0, 0, 0, 0}, a2{0, 0, 0, 0};
+        float xf = 0, yf = 0, zf = 0, rc2f = 0;
         if (active) {
             while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
             gi = s_ibeg[c] + (ii - s_ipre[c]);
@@ -297,7 +315,17 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
                            A.por2[gi], A.h[gi]);
             const int cf = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : cell_coord<R>(I.y, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
             lf = cf - f0;   // 0 .. G-1
+            xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
+            if (LOCAL) rc2f = far ? __int_as_float(0x7f800000) : __double2float_ru((double)I.rc2 * (1.0 + 1.0 / 32768.0));
+            else rc2f = (float)I.rc2;
         }
+        auto test = [&](const float4& p) -> bool {
+            const float dxf = xf - p.x, dyf = yf - p.y, dzf = zf - p.z;
+            float r2f;
+            if (LOCAL) { r2f = dxf * dxf + dyf * dyf; if (DIM == 3) r2f += dzf * dzf; return r2f <= rc2f; }
+            r2f = dist2<DIM, float>(dxf, dyf, dzf);
+            return r2f < rc2f && r2f > 0.0f;
+        };
         // scan cursor over this particle's 9 (3) runs
         int run = 0, jv = 0, jend = 0;
         constexpr int NRUN = DIM == 3 ? 9 : 3;
@@ -309,34 +337,57 @@ __global__ void __launch_bounds__(NT) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> 
         };
         bool done = !active;
         if (active) open_run(0);
+        unsigned short* const my_list = s_list + tid;
         while (true) {
-            // ---- phase 1: exact cutoff test on staged candidates, compact hits into the private list
+            // ---- phase 1: pre-filter on staged f32 coordinates, compact hits into the private list
             int cnt = 0;
             if (!done) {
+                unsigned short* lp = my_list;              // next free list slot (stride NT)
+                unsigned short* const lend = my_list + LC * NT;
                 while (true) {
-                    while (jv < jend && cnt < LC) {
-                        const R dx = I.x - s_x[jv], dy = I.y - s_y[jv], dz = DIM == 3 ? I.z - s_z[jv] : (R)0;
-                        const R r2 = dist2<DIM, R>(dx, dy, dz);
-                        if (r2 < I.rc2 && r2 > (R)0) { s_list[cnt * NT + tid] = (unsigned short)jv; ++cnt; }
+                    while (jv + 4 <= jend && lp + 4 * NT <= lend) {          // 4 candidates in flight
+                        const float4 p0 = s_p4[jv], p1 = s_p4[jv + 1], p2 = s_p4[jv + 2], p3 = s_p4[jv + 3];
+                        const bool h0 = test(p0), h1 = test(p1), h2 = test(p2), h3 = test(p3);
+                        if (h0) { *lp = (unsigned short)jv; lp += NT; }
+                        if (h1) { *lp = (unsigned short)(jv + 1); lp += NT; }
+                        if (h2) { *lp = (unsigned short)(jv + 2); lp += NT; }
+                        if (h3) { *lp = (unsigned short)(jv + 3); lp += NT; }
+                        jv += 4;
+                    }
+                    while (jv < jend && lp < lend) {
+                        if (test(s_p4[jv])) { *lp = (unsigned short)jv; lp += NT; }
                         ++jv;
                     }
                     if (jv < jend) break;          // list full: drain, then resume here
                     if (++run == NRUN) { done = true; break; }
                     open_run(run);
                 }
+                cnt = (int)(lp - my_list) / NT;
             }
-            // ---- phase 2: the pair body on hits only
-            for (int k = 0; k < cnt; ++k) {
-                const int j = s_list[k * NT + tid];
-                const R dx = I.x - s_x[j], dy = I.y - s_y[j], dz = DIM == 3 ? I.z - s_z[j] : (R)0;
-                const R r2 = dist2<DIM, R>(dx, dy, dz);
-                pair_body<R, DIM, CONT, MOM>(C, I, dx, dy, dz, r2, s_u[j], s_v[j], DIM == 3 ? s_w[j] : (R)0, s_rho[j], s_m[j], s_por2[j], a);
+            // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
+            for (int k = 0; k < cnt; k += 2) {
+                const bool v1 = k + 1 < cnt;
+                const int j0 = __float_as_int(s_p4[my_list[k * NT]].w);
+                const int j1 = v1 ? __float_as_int(s_p4[my_list[(k + 1) * NT]].w) : j0;
+                const R dx0 = I.x - A.x[j0], dy0 = I.y - A.y[j0], dz0 = DIM == 3 ? I.z - A.z[j0] : (R)0;
+                const R dx1 = I.x - A.x[j1], dy1 = I.y - A.y[j1], dz1 = DIM == 3 ? I.z - A.z[j1] : (R)0;
+                R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
+                const bool in0 = r20 < I.rc2 && r20 > (R)0;            // the exact test (the set is defined here)
+                const bool in1 = v1 && r21 < I.rc2 && r21 > (R)0;
+                r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
+                const R m0 = in0 ? A.m[j0] : (R)0, m1 = in1 ? A.m[j1] : (R)0;
+                pair_body<R, DIM, CONT, MOM>(C, I, dx0, dy0, dz0, r20, A.u[j0], A.v[j0], DIM == 3 ? A.w[j0] : (R)0, A.rho[j0], m0, A.por2[j0], a);
+                pair_body<R, DIM, CONT, MOM>(C, I, dx1, dy1, dz1, r21, A.u[j1], A.v[j1], DIM == 3 ? A.w[j1] : (R)0, A.rho[j1], m1, A.por2[j1], a2);
             }
             if (__all_sync(0xffffffffu, done)) break;
         }
-        if (active) store_acc<R, DIM, CONT, MOM>(A, C, gi, a);
+        if (active) {
+            a.au += a2.au; a.av += a2.av; a.aw += a2.aw; a.arho += a2.arho;
+            store_acc<R, DIM, CONT, MOM>(A, C, gi, a);
+        }
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // variant 2 (default): shared-memory tiles, ONE WARP PER CELL, candidate-parallel scan
@@ -447,7 +498,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) k_wcsph_cellwarp(GridDev<R> g, W
     }
     if (ni == 0) return;
     const int M = s_voff[NR];
-    if (M > JC) {   // tile denser than the staging buffer: exact per-particle gather for its particles
+    if (M > min(JC, T.jcap)) {   // tile denser than the staging buffer: exact per-particle gather for its particles
         for (int c = 0; c < NI; ++c) {
             const int lx = c / BB, ly = c - lx * BB;
             const int q = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
@@ -631,46 +682,36 @@ pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
     return PST_OK;
 }
 
-// VARIANT 1: warp-per-cell (2 CTAs/SM, no per-thread lists); VARIANT 2: per-thread hit lists (1 CTA/SM)
-template <class R, int DIM, int VARIANT>
+// VARIANT 1: warp-per-cell (no per-thread lists); VARIANT 2: thread-per-particle with private hit lists.  Both 2 CTAs/SM.
+template <class R, int DIM, int VARIANT, int TA>
 pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
-    constexpr int TA = 2, TB = 2, NT = VARIANT == 1 ? 192 : 256;
+    constexpr int TB = 2, NT = VARIANT == 1 ? 192 : 256;
     using D = TileDims<DIM, TA, TB>;
     const PstGrid& g = ctx->grid;
     const int nf = DIM == 3 ? g.n[2] : g.n[1];
     double ppc = pst_param(ctx, "_ppc", 0.0);      // mean occupancy of the occupied cells (measured by k_bounds)
     if (!(ppc > 0)) ppc = DIM == 3 ? 14.0 : 6.0;
-    const size_t budget = (size_t)pst_option(ctx, "tile_smem_kb", VARIANT == 1 ? 113 : 200) * 1024;
     TileShape T;
     T.lcap = pst_option(ctx, "tile_lcap", DIM == 3 ? 80 : 32);
-    const size_t fixed = VARIANT == 1 ? (size_t)(NT / 32) * 512 * sizeof(unsigned short) * 2 : (size_t)T.lcap * NT * sizeof(unsigned short);
+    const int jc_max = VARIANT == 1 ? kCellwarpJcap<R, NT>() : kListsJcap;
     const int user_G = pst_option(ctx, "tile_g", 0);
     int G = user_G;
     if (G <= 0) {
-        if (VARIANT == 1) {   // deepest tile whose staged runs fit the buffer with 12 % headroom
-            const double jc = (double)kCellwarpJcap<R, NT>();
-            G = (int)std::floor(jc / (1.12 * D::NR * ppc)) - 2;
-        } else {              // one thread per particle
-            G = (int)std::floor(0.95 * NT / (D::NI * ppc));
-        }
+        if (VARIANT == 1) G = (int)std::floor(jc_max / (1.12 * D::NR * ppc)) - 2;   // deepest tile that fits with 12 % headroom
+        else G = (int)std::floor(0.95 * NT / (D::NI * ppc));                        // one thread per particle
     }
     G = std::min(std::max(G, 1), std::max(1, nf));
-    if (VARIANT == 1) G = std::min(G, (256 - 2 * D::NR - 2 * D::NI - 3) / D::NR - 3);   // boundary tables must fit their 1 KB
+    G = std::min(G, (256 - 2 * D::NR - 2 * D::NI - 3) / D::NR - 3);   // boundary tables stay within 1 KB
     T.G = G;
     T.tiles[0] = (g.n[0] + TA - 1) / TA;
     T.tiles[1] = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
     T.tiles[2] = (nf + G - 1) / G;
+    // "tile_jcap" (tests): pretend the staging buffer is smaller, to force the in-kernel exact fallback
+    T.jcap = std::min(jc_max, std::max(0, pst_option(ctx, "tile_jcap", jc_max)));
     const size_t ints = ((size_t)(D::NR * (G + 3) + D::NR + D::NR + 1 + D::NI + D::NI + 1) * sizeof(int) + 15) & ~(size_t)15;
-    if (ints + fixed + 9 * sizeof(R) * 64 > budget) return pst_fail(ctx, PST_EINVAL, "tile_smem_kb too small");
-    int jcap = (int)((budget - ints - fixed) / (9 * sizeof(R)));
-    jcap = std::min(jcap, 65535) & ~1;   // hit lists / queues hold 16-bit staged indices
-    size_t smem = ints + (size_t)jcap * 9 * sizeof(R) + fixed;
-    if (VARIANT == 1) {
-        if (ints > 1024) return pst_fail(ctx, PST_EINVAL, "tile_g too large for the warp-per-cell kernel");
-        jcap = kCellwarpJcap<R, NT>();
-        smem = 113 * 1024;
-    }
-    T.jcap = jcap;
+    const size_t smem = VARIANT == 1 ? (size_t)113 * 1024
+                                     : ints + 4 * sizeof(double) + (size_t)kListsJcap * sizeof(float4) + (size_t)T.lcap * NT * sizeof(unsigned short);
+    if (smem > 227 * 1024) return pst_fail(ctx, PST_EINVAL, "tile_lcap too large");
     if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, true>(ctx, T, smem);
     if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, false>(ctx, T, smem);
     return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, false, true>(ctx, T, smem);
@@ -678,9 +719,9 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
 
 template <class R, int DIM, bool MORTON>
 pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
-    const int variant = pst_option(ctx, "force_kernel", 1);
-    if (variant == 1 && !MORTON) return launch_tiled<R, DIM, 1>(ctx, cont, mom);
-    if (variant == 2 && !MORTON) return launch_tiled<R, DIM, 2>(ctx, cont, mom);
+    const int variant = pst_option(ctx, "force_kernel", 2);   // 2 = thread-per-particle lists (fastest measured), 1 = warp-per-cell, 0 = gather
+    if (variant == 1 && !MORTON) return launch_tiled<R, DIM, 1, 2>(ctx, cont, mom);
+    if (variant == 2 && !MORTON) return pst_option(ctx, "tile_ta", 2) == 3 ? launch_tiled<R, DIM, 2, 3>(ctx, cont, mom) : launch_tiled<R, DIM, 2, 2>(ctx, cont, mom);
     return launch_gather<R, DIM, MORTON>(ctx, cont, mom);
 }
 

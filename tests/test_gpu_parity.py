@@ -24,7 +24,7 @@ def _ctx(block, real, key="linear", **kw):
     return ctx
 
 
-def _wcsph_gpu(block, real, key="linear", variant=1, names=("tait_eos", "continuity", "momentum"), opts=None):
+def _wcsph_gpu(block, real, key="linear", variant=2, names=("tait_eos", "continuity", "momentum"), opts=None):
     b = block.astype(real)
     with _ctx(b, real, key) as ctx:
         ctx.set_option("force_kernel", variant)
@@ -106,7 +106,7 @@ def test_neighbour_set_particles_outside_box():
 # WCSPH: EOS + continuity + momentum, one evaluation
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("real", REALS)
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_wcsph_3d(real, variant):
     b = synth.wcsph_block_3d(20, 18, 22).shuffled()
     br = b.astype(real)
@@ -119,7 +119,7 @@ def test_wcsph_3d(real, variant):
 
 
 @pytest.mark.parametrize("real", REALS)
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_wcsph_2d_dambreak(real, variant):
     b = synth.wcsph_dambreak_2d(dx=0.02).shuffled()
     br = b.astype(real)
@@ -163,13 +163,14 @@ def test_wcsph_general_gamma():
         assert_close(got[k], ref[k], f"gamma {k}")
 
 
-@pytest.mark.parametrize("opts", [{"tile_g": 1}, {"tile_g": 3, "tile_lcap": 8}, {"tile_g": 7, "tile_smem_kb": 24, "tile_lcap": 16}, {"tile_g": 64}])
-def test_wcsph_tiled_edge_shapes(opts):
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("opts", [{"tile_g": 1}, {"tile_g": 3, "tile_lcap": 8}, {"tile_g": 4, "tile_jcap": 100, "tile_lcap": 16}, {"tile_g": 64}])
+def test_wcsph_tiled_edge_shapes(opts, variant):
     """Tile depth 1, tiny hit lists (forces mid-scan drains), a staging buffer that overflows (exact
     per-particle path inside the tiled kernel) and a tile deeper than the grid must all agree."""
     b = synth.wcsph_block_3d(15, 11, 16).shuffled()
     ref = orc.wcsph(3, b.params, b.arrays)
-    got, _ = _wcsph_gpu(b, np.float64, variant=1, opts=opts)
+    got, _ = _wcsph_gpu(b, np.float64, variant=variant, opts=opts)
     for k in ("au", "av", "aw", "arho"):
         assert_close(got[k], ref[k], f"tiled {opts} {k}")
 
@@ -196,7 +197,7 @@ def test_wcsph_tiny_and_degenerate():
              "w": np.zeros(n), "rho": np.full(n, 1001.0), "m": np.full(n, 1e-4), "h": np.full(n, 0.006), "tag": np.zeros(n, np.int32)}
         blk = synth.Block("tiny", 3, "wcsph", a, P, (0, 0, 0), (1, 1, 1), 0.012 * synth.CELL_MARGIN)
         ref = orc.wcsph(3, P, a)
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             got, _ = _wcsph_gpu(blk, np.float64, variant=variant)
             for k in ("au", "av", "aw", "arho"):
                 assert_close(got[k], ref[k], f"tiny n={n} {k}")
