@@ -342,27 +342,32 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
             // ---- phase 1: pre-filter on staged f32 coordinates, compact hits into the private list
             int cnt = 0;
             if (!done) {
-                unsigned short* lp = my_list;              // next free list slot (stride NT)
-                unsigned short* const lend = my_list + LC * NT;
+                // private list = column `tid` of s_list (stride NT): one running shared-memory byte address
+                const unsigned la0 = (unsigned)__cvta_generic_to_shared(my_list), lend = la0 + (unsigned)(LC * NT * 2);
+                unsigned la = la0;
+                // (no per-store "memory" clobber: it would pin the next LDS.128 batch behind every append; one compiler
+                // barrier after the scan orders the list stores before phase 2 reads them)
+                auto push = [&](int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(la), "h"((unsigned short)v)); la += 2 * NT; };
                 while (true) {
-                    while (jv + 4 <= jend && lp + 4 * NT <= lend) {          // 4 candidates in flight
+                    while (jv + 4 <= jend && la + 8 * NT <= lend) {          // 4 candidates in flight
                         const float4 p0 = s_p4[jv], p1 = s_p4[jv + 1], p2 = s_p4[jv + 2], p3 = s_p4[jv + 3];
                         const bool h0 = test(p0), h1 = test(p1), h2 = test(p2), h3 = test(p3);
-                        if (h0) { *lp = (unsigned short)jv; lp += NT; }
-                        if (h1) { *lp = (unsigned short)(jv + 1); lp += NT; }
-                        if (h2) { *lp = (unsigned short)(jv + 2); lp += NT; }
-                        if (h3) { *lp = (unsigned short)(jv + 3); lp += NT; }
+                        if (h0) push(jv);
+                        if (h1) push(jv + 1);
+                        if (h2) push(jv + 2);
+                        if (h3) push(jv + 3);
                         jv += 4;
                     }
-                    while (jv < jend && lp < lend) {
-                        if (test(s_p4[jv])) { *lp = (unsigned short)jv; lp += NT; }
+                    while (jv < jend && la < lend) {
+                        if (test(s_p4[jv])) push(jv);
                         ++jv;
                     }
                     if (jv < jend) break;          // list full: drain, then resume here
                     if (++run == NRUN) { done = true; break; }
                     open_run(run);
                 }
-                cnt = (int)(lp - my_list) / NT;
+                cnt = (int)((la - la0) / (2 * NT));
+                asm volatile("" ::: "memory");
             }
             // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
             for (int k = 0; k < cnt; k += 2) {
@@ -671,12 +676,10 @@ pst_status launch_gather(pst_ctx* ctx, bool cont, bool mom) {
 
 template <class R, int DIM, int TA, int TB, int NT, int VARIANT, bool CONT, bool MOM>
 pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
-    auto kern = VARIANT == 1 ? k_wcsph_cellwarp<R, DIM, TA, TB, NT, CONT, MOM> : k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM>;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    void (*kern)(GridDev<R>, WcsphConst<R>, ForceArgs<R>, TileShape);
+    if (VARIANT == 1) kern = k_wcsph_cellwarp<R, DIM, TA, TB, NT, CONT, MOM>;
+    else kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM>;
+    PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const unsigned grid = (unsigned)T.tiles[0] * T.tiles[1] * T.tiles[2];
     PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), make_args<R>(ctx), T);
     return PST_OK;
