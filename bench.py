@@ -353,18 +353,21 @@ def main():
         h2d = sum(v.nbytes for v in hin.values()); d2h = sum(v.nbytes for v in hout.values())
 
         def e2e_step():
+            # the public asynchronous path: H2D of this step's state and D2H of the previous step's rates ride the two
+            # copy engines (PCIe is full duplex) while the compute stream works; every byte still crosses every step
             for k in ins:
-                ctx.upload_ptr(k, hin[k].ctypes.data)
+                ctx.upload_async(k, hin[k].ctypes.data)
             step()
+            ctx.wait_transfers()                 # previous step's rates have landed: the host may consume them now
             for k in outs:
-                ctx.download_ptr(k, hout[k].ctypes.data)
+                ctx.download_async(k, hout[k].ctypes.data)
         e2e_steps = max(3, min(args.steps, 10))
         e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
-        barrier()
+        barrier()                                # pst_sync: all uploads consumed, all rates of the last step on the host
         te = time.perf_counter() - t0
         if world > 1:
             tt = torch.tensor([te], device="cuda", dtype=torch.float64)
@@ -372,7 +375,7 @@ def main():
             te = float(tt[0])
         e2e = {"value": n_total * e2e_steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e2e_steps, "ms_per_step": te / e2e_steps * 1e3,
-               "path": "pst_upload(state, pinned host) -> pst_build_neighbours -> pst_apply -> pst_download(rates, pinned host)"}
+               "path": "pst_upload_async(7 state arrays, pinned host) -> pst_build_neighbours -> pst_apply -> pst_download_async(rates, pinned host), pst_sync at the end"}
         pin.free()
 
     if rank == 0:

@@ -112,7 +112,14 @@ PST_API pst_status pst_array(pst_ctx* ctx, const char* name, void** dev_ptr, siz
 /* host buffers hold rows * n elements, row-major, particle index = id */
 PST_API pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n);
 PST_API pst_status pst_download(pst_ctx* ctx, const char* name, void* host, size_t n);
-/* pinned host memory for fast transfers (optional; any host memory works) */
+/* Asynchronous variants: copies run on dedicated H2D / D2H streams and overlap the compute stream (and each other:
+ * PCIe is full duplex).  `host` must be pinned (pst_host_alloc) and must stay untouched until pst_sync (uploads) or
+ * pst_wait_transfers / pst_sync (downloads).  Fall back to the synchronous path for multi-row arrays. */
+PST_API pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, size_t n);
+PST_API pst_status pst_download_async(pst_ctx* ctx, const char* name, void* host, size_t n);
+/* wait until every pst_download_async issued so far has landed in host memory (does not wait for compute) */
+PST_API pst_status pst_wait_transfers(pst_ctx* ctx);
+/* pinned host memory for fast transfers (optional for the synchronous calls; any host memory works there) */
 PST_API void* pst_host_alloc(size_t bytes);
 PST_API void pst_host_free(void* p);
 

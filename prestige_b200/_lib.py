@@ -31,7 +31,7 @@ class PstConfig(C.Structure):
 SYMBOLS = [
     "pst_version", "pst_create", "pst_destroy", "pst_last_error", "pst_stream", "pst_sync", "pst_set_param",
     "pst_get_param", "pst_set_count", "pst_get_count", "pst_array_create", "pst_array", "pst_upload",
-    "pst_download", "pst_host_alloc", "pst_host_free", "pst_build_neighbours", "pst_apply", "pst_dump_pairs",
+    "pst_download", "pst_upload_async", "pst_download_async", "pst_wait_transfers", "pst_host_alloc", "pst_host_free", "pst_build_neighbours", "pst_apply", "pst_dump_pairs",
     "pst_step", "pst_integrate", "pst_get_stat", "pst_set_option", "pst_comm_unique_id", "pst_comm_init",
     "pst_halo_exchange",
 ]
@@ -64,6 +64,9 @@ def load() -> C.CDLL:
     lib.pst_array.restype = st
     lib.pst_upload.argtypes = [vp, cp, vp, C.c_size_t]; lib.pst_upload.restype = st
     lib.pst_download.argtypes = [vp, cp, vp, C.c_size_t]; lib.pst_download.restype = st
+    lib.pst_upload_async.argtypes = [vp, cp, vp, C.c_size_t]; lib.pst_upload_async.restype = st
+    lib.pst_download_async.argtypes = [vp, cp, vp, C.c_size_t]; lib.pst_download_async.restype = st
+    lib.pst_wait_transfers.argtypes = [vp]; lib.pst_wait_transfers.restype = st
     lib.pst_host_alloc.argtypes = [C.c_size_t]; lib.pst_host_alloc.restype = vp
     lib.pst_host_free.argtypes = [vp]; lib.pst_host_free.restype = None
     lib.pst_build_neighbours.argtypes = [vp]; lib.pst_build_neighbours.restype = st

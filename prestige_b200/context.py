@@ -126,6 +126,17 @@ class Context:
     def download_ptr(self, name: str, ptr: int):
         self._ck(self._lib.pst_download(self._h, name.encode(), C.c_void_p(ptr), self.n))
 
+    def upload_async(self, name: str, ptr: int):
+        """Asynchronous upload from PINNED host memory (pst_host_alloc); valid data required until sync()."""
+        self._ck(self._lib.pst_upload_async(self._h, name.encode(), C.c_void_p(ptr), self.n))
+
+    def download_async(self, name: str, ptr: int):
+        """Asynchronous download into PINNED host memory; complete after wait_transfers() or sync()."""
+        self._ck(self._lib.pst_download_async(self._h, name.encode(), C.c_void_p(ptr), self.n))
+
+    def wait_transfers(self):
+        self._ck(self._lib.pst_wait_transfers(self._h))
+
     def load_block(self, block, arrays=None):
         """set_count + params + upload of every array of a synth.Block this context knows."""
         self.set_count(block.n)

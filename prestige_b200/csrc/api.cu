@@ -92,7 +92,8 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
     ctx->ghost_cap = cfg->ghost_capacity;
     auto bail = [&](pst_status s) { g_create_err = ctx->err; pst_destroy(ctx); return s; };
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         pst_fail(ctx, PST_ECUDA, "cudaStreamCreate failed");
         return bail(PST_ECUDA);
     }
@@ -178,7 +179,13 @@ void pst_destroy(pst_ctx* ctx) {
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->h2d_stream) { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamDestroy(ctx->h2d_stream); }
+    if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
+    for (int k = 0; k < pst_ctx::kRing; ++k) {
+        cudaFree(ctx->ring[k]);
+        if (ctx->ring_free[k]) cudaEventDestroy(ctx->ring_free[k]);
+        if (ctx->ring_ready[k]) cudaEventDestroy(ctx->ring_ready[k]);
+    }
     delete ctx;
 }
 
@@ -199,7 +206,84 @@ static pst_status check_flags(pst_ctx* ctx) {
 pst_status pst_sync(pst_ctx* ctx) {
     if (!ctx) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    return check_flags(ctx);
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->h2d_stream));
+    PST_TRY(check_flags(ctx));           // synchronises the compute stream
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+    return PST_OK;
+}
+
+pst_status pst_wait_transfers(pst_ctx* ctx) {
+    if (!ctx) return PST_EINVAL;
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+    return PST_OK;
+}
+
+// next staging buffer of the ring; the stream `user` is made to wait until the buffer's previous use is over
+static pst_status ring_acquire(pst_ctx* ctx, cudaStream_t user, bool upload, int* idx) {
+    // separate sub-rings, so an upload never waits for a download's D2H (and vice versa)
+    constexpr int kUp = 24, kDown = pst_ctx::kRing - kUp;
+    int k;
+    if (upload) { k = ctx->ring_next_up; ctx->ring_next_up = (k + 1) % kUp; }
+    else { k = kUp + ctx->ring_next_down; ctx->ring_next_down = (ctx->ring_next_down + 1) % kDown; }
+    if (!ctx->ring[k]) {
+        const size_t bytes = (ctx->capacity + 2 * ctx->ghost_cap) * 8;
+        if (cudaMalloc((void**)&ctx->ring[k], bytes) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "staging ring buffer (%zu bytes)", bytes);
+        PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_free[k], cudaEventDisableTiming));
+        PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_ready[k], cudaEventDisableTiming));
+    } else {
+        PST_CUDA(ctx, cudaStreamWaitEvent(user, ctx->ring_free[k], 0));
+    }
+    *idx = k;
+    return PST_OK;
+}
+
+// Asynchronous transfers: the copy engines run on their own streams (H2D and D2H are full duplex) and overlap the
+// kernels of the compute stream.  `host` must be pinned (pst_host_alloc) and must not be touched until pst_sync
+// (uploads) / pst_wait_transfers or pst_sync (downloads).
+pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, size_t n) {
+    if (!ctx || !name || !host) return PST_EINVAL;
+    PstArray* a = pst_find(ctx, name);
+    if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
+    if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
+    if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
+    if (!ctx->ordered || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / history rows: plain path
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int k = 0;
+    PST_TRY(ring_acquire(ctx, ctx->h2d_stream, true, &k));
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->ring[k], host, n * a->esize, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    PST_CUDA(ctx, cudaEventRecord(ctx->ring_ready[k], ctx->h2d_stream));
+    PST_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ring_ready[k], 0));
+    char* saved = ctx->stage;
+    ctx->stage = ctx->ring[k];
+    const pst_status st = pst_reorder_upload(ctx, a, 0, n);
+    ctx->stage = saved;
+    PST_TRY(st);
+    PST_CUDA(ctx, cudaEventRecord(ctx->ring_free[k], ctx->stream));
+    if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
+    if (a->name == "rho") ctx->eos_valid = false;
+    return PST_OK;
+}
+
+pst_status pst_download_async(pst_ctx* ctx, const char* name, void* host, size_t n) {
+    if (!ctx || !name || !host) return PST_EINVAL;
+    PstArray* a = pst_find(ctx, name);
+    if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
+    if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "download '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
+    if (!ctx->ordered || a->rows != 1 || a->name == "id") return pst_download(ctx, name, host, n);
+    PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int k = 0;
+    PST_TRY(ring_acquire(ctx, ctx->stream, false, &k));
+    char* saved = ctx->stage;
+    ctx->stage = ctx->ring[k];
+    const pst_status st = pst_reorder_download(ctx, a, 0, n);
+    ctx->stage = saved;
+    PST_TRY(st);
+    PST_CUDA(ctx, cudaEventRecord(ctx->ring_ready[k], ctx->stream));
+    PST_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ring_ready[k], 0));
+    PST_CUDA(ctx, cudaMemcpyAsync(host, ctx->ring[k], n * a->esize, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    PST_CUDA(ctx, cudaEventRecord(ctx->ring_free[k], ctx->d2h_stream));
+    return PST_OK;
 }
 
 pst_status pst_set_param(pst_ctx* ctx, const char* name, double value) {

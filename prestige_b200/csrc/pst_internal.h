@@ -43,7 +43,12 @@ struct pst_ctx {
     bool f64 = true;
     int dim = 3;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pst_upload_async / pst_download_async
+    static constexpr int kRing = 32;                           // staging slots of the async transfers (lazily allocated): [0,24) uploads, [24,32) downloads
+    char* ring[kRing] = {};
+    cudaEvent_t ring_free[kRing] = {};                         // buffer k may be overwritten once this event completed
+    cudaEvent_t ring_ready[kRing] = {};                        // producer -> consumer hand-over
+    int ring_next_up = 0, ring_next_down = 0;
     std::vector<PstArray> arrays;
     std::map<std::string, int> index;
     std::map<std::string, double> params;
