@@ -35,8 +35,89 @@ struct DemArgs {
     int n;
 };
 
+// one contact: normal + tangential law, history lookup by stable partner id, torque.  Shared by both kernels.
+template <class R>
+__device__ __forceinline__ void dem_contact(const DemConst<R>& C, const DemArgs<R>& A, int s, int j, R xi, R yi, R zi, R ui, R vi, R wi, R ri,
+                                            R mi, R owx, R owy, R owz, int nold, R& fx, R& fy, R& fz, R& tx, R& ty, R& tz, int& cnt) {
+    const R dx = xi - A.x[j], dy = yi - A.y[j], dz = zi - A.z[j];
+    const R r2 = dist2<3, R>(dx, dy, dz);
+    const R rj = A.rad[j];
+    const R rs = add_rn(ri, rj);
+    const R r = sqrt(r2);
+    const R rinv = (R)1 / r;
+    const R nx = dx * rinv, ny = dy * rinv, nz = dz * rinv;
+    const R delta = rs - r;
+    // R_i w_i + R_j w_j as a commutative sum of two rounded products (no FMA), so both sides of the
+    // contact see the same bits and F_ji = -F_ij exactly
+    const R ox = add_rn(owx, mul_rn(rj, A.wx[j])), oy = add_rn(owy, mul_rn(rj, A.wy[j])), oz = add_rn(owz, mul_rn(rj, A.wz[j]));
+    const R vcx = (ui - A.u[j]) - (oy * nz - oz * ny);
+    const R vcy = (vi - A.v[j]) - (oz * nx - ox * nz);
+    const R vcz = (wi - A.w[j]) - (ox * ny - oy * nx);
+    const R vn = vcx * nx + vcy * ny + vcz * nz;
+    const R vtx = vcx - vn * nx, vty = vcy - vn * ny, vtz = vcz - vn * nz;
+    R kn = C.kn, gn = C.gn, kt = C.kt, gt = C.gt;
+    if (C.model == 1) {
+        const R mj = A.m[j];
+        const R Rs = ri * rj / rs;
+        const R ms = mi * mj / (mi + mj);
+        const R sq = sqrt(Rs * delta);
+        const R Sn = (R)2 * C.Estar * sq, St = (R)8 * C.Gstar * sq;
+        kn = (R)(4.0 / 3.0) * C.Estar * sq;
+        kt = St;
+        gn = C.damp_c * sqrt(Sn * ms);
+        gt = C.damp_c * sqrt(St * ms);
+    }
+    const R fnm = kn * delta - gn * vn;
+    // history lookup by stable partner id (new contact => xi = 0); branch-free scan so the slot loads overlap
+    const uint32_t pid = A.id[j];
+    int slot = -1;
+    for (int k = 0; k < nold; ++k)
+        if (A.hid_in[(size_t)k * A.stride + s] == pid) slot = k;
+    R hx = 0, hy = 0, hz = 0;
+    if (slot >= 0) {
+        const size_t o = (size_t)slot * A.stride + s;
+        hx = A.hx_in[o]; hy = A.hy_in[o]; hz = A.hz_in[o];
+    }
+    const R xn = hx * nx + hy * ny + hz * nz;
+    hx = hx - xn * nx + vtx * C.dt;
+    hy = hy - xn * ny + vty * C.dt;
+    hz = hz - xn * nz + vtz * C.dt;
+    R ftx = -kt * hx - gt * vtx, fty = -kt * hy - gt * vty, ftz = -kt * hz - gt * vtz;
+    const R ftm = sqrt(ftx * ftx + fty * fty + ftz * ftz);
+    const R fmax = C.mu * fabs(fnm);
+    if (ftm > fmax) {
+        const R sc = fmax / ftm;
+        ftx *= sc; fty *= sc; ftz *= sc;
+        const R ikt = (R)1 / kt;
+        hx = -(ftx + gt * vtx) * ikt; hy = -(fty + gt * vty) * ikt; hz = -(ftz + gt * vtz) * ikt;
+    }
+    fx += fnm * nx + ftx; fy += fnm * ny + fty; fz += fnm * nz + ftz;
+    const R lx = -ri * nx, ly = -ri * ny, lz = -ri * nz;
+    tx += ly * ftz - lz * fty;
+    ty += lz * ftx - lx * ftz;
+    tz += lx * fty - ly * ftx;
+    if (cnt < C.K) {
+        const size_t o = (size_t)cnt * A.stride + s;
+        A.hid_out[o] = pid; A.hx_out[o] = hx; A.hy_out[o] = hy; A.hz_out[o] = hz;
+    }
+    ++cnt;
+}
+
+template <class R>
+__device__ __forceinline__ void dem_finish(const DemConst<R>& C, const DemArgs<R>& A, int s, int cnt, R fx, R fy, R fz, R tx, R ty, R tz) {
+    if (cnt > C.K) {            // never silent truncation: PST_EOVERFLOW at the next sync
+        atomicExch(&A.flags[0], 1);
+        atomicMax(&A.flags[1], cnt);
+        cnt = C.K;
+    }
+    A.hn_out[s] = cnt;
+    A.fx[s] = fx; A.fy[s] = fy; A.fz[s] = fz;
+    A.tx[s] = tx; A.ty[s] = ty; A.tz[s] = tz;
+}
+
+// generic kernel (any key mode): contact body evaluated inside the candidate loop
 template <class R, bool MORTON>
-__global__ void __launch_bounds__(kThreads) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
+__global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
     const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
@@ -53,74 +134,68 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces(GridDev<R> g, DemConst<
         for (int j = b; j < e; ++j) {
             const R dx = xi - A.x[j], dy = yi - A.y[j], dz = zi - A.z[j];
             const R r2 = dist2<3, R>(dx, dy, dz);
-            const R rj = A.rad[j];
-            const R rs = add_rn(ri, rj);
+            const R rs = add_rn(ri, A.rad[j]);
             if (!(r2 < mul_rn(rs, rs)) || !(r2 > (R)0) || j == s) continue;
-            const R r = sqrt(r2);
-            const R rinv = (R)1 / r;
-            const R nx = dx * rinv, ny = dy * rinv, nz = dz * rinv;
-            const R delta = rs - r;
-            // R_i w_i + R_j w_j as a commutative sum of two rounded products (no FMA), so both sides of the
-            // contact see the same bits and F_ji = -F_ij exactly
-            const R ox = add_rn(owx, mul_rn(rj, A.wx[j])), oy = add_rn(owy, mul_rn(rj, A.wy[j])), oz = add_rn(owz, mul_rn(rj, A.wz[j]));
-            const R vcx = (ui - A.u[j]) - (oy * nz - oz * ny);
-            const R vcy = (vi - A.v[j]) - (oz * nx - ox * nz);
-            const R vcz = (wi - A.w[j]) - (ox * ny - oy * nx);
-            const R vn = vcx * nx + vcy * ny + vcz * nz;
-            const R vtx = vcx - vn * nx, vty = vcy - vn * ny, vtz = vcz - vn * nz;
-            R kn = C.kn, gn = C.gn, kt = C.kt, gt = C.gt;
-            if (C.model == 1) {
-                const R mj = A.m[j];
-                const R Rs = ri * rj / rs;
-                const R ms = mi * mj / (mi + mj);
-                const R sq = sqrt(Rs * delta);
-                const R Sn = (R)2 * C.Estar * sq, St = (R)8 * C.Gstar * sq;
-                kn = (R)(4.0 / 3.0) * C.Estar * sq;
-                kt = St;
-                gn = C.damp_c * sqrt(Sn * ms);
-                gt = C.damp_c * sqrt(St * ms);
-            }
-            const R fnm = kn * delta - gn * vn;
-            // history lookup by stable partner id (new contact => xi = 0)
-            const uint32_t pid = A.id[j];
-            R hx = 0, hy = 0, hz = 0;
-            for (int k = 0; k < nold; ++k) {
-                const size_t o = (size_t)k * A.stride + s;
-                if (A.hid_in[o] == pid) { hx = A.hx_in[o]; hy = A.hy_in[o]; hz = A.hz_in[o]; break; }
-            }
-            const R xn = hx * nx + hy * ny + hz * nz;
-            hx = hx - xn * nx + vtx * C.dt;
-            hy = hy - xn * ny + vty * C.dt;
-            hz = hz - xn * nz + vtz * C.dt;
-            R ftx = -kt * hx - gt * vtx, fty = -kt * hy - gt * vty, ftz = -kt * hz - gt * vtz;
-            const R ftm = sqrt(ftx * ftx + fty * fty + ftz * ftz);
-            const R fmax = C.mu * fabs(fnm);
-            if (ftm > fmax) {
-                const R sc = fmax / ftm;
-                ftx *= sc; fty *= sc; ftz *= sc;
-                const R ikt = (R)1 / kt;
-                hx = -(ftx + gt * vtx) * ikt; hy = -(fty + gt * vty) * ikt; hz = -(ftz + gt * vtz) * ikt;
-            }
-            fx += fnm * nx + ftx; fy += fnm * ny + fty; fz += fnm * nz + ftz;
-            const R lx = -ri * nx, ly = -ri * ny, lz = -ri * nz;
-            tx += ly * ftz - lz * fty;
-            ty += lz * ftx - lx * ftz;
-            tz += lx * fty - ly * ftx;
-            if (cnt < C.K) {
-                const size_t o = (size_t)cnt * A.stride + s;
-                A.hid_out[o] = pid; A.hx_out[o] = hx; A.hy_out[o] = hy; A.hz_out[o] = hz;
-            }
-            ++cnt;
+            dem_contact<R>(C, A, s, j, xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, fx, fy, fz, tx, ty, tz, cnt);
         }
     });
-    if (cnt > C.K) {            // never silent truncation: PST_EOVERFLOW at the next sync
-        atomicExch(&A.flags[0], 1);
-        atomicMax(&A.flags[1], cnt);
-        cnt = C.K;
+    dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
+}
+
+// linear keys: (1) all 18 run bounds are fetched at once, (2) the contact TEST runs over the candidates four
+// at a time with their 16 loads in flight together and only records the hits, (3) the heavy contact body then
+// runs on the recorded hits.  The kernel is a latency-bound gather, so the win is memory-level parallelism.
+template <class R>
+__global__ void __launch_bounds__(kThreads) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n) return;
+    const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
+    const R ri = A.rad[s];
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1);
+    const int zl = max(cz - 1, 0), zh = min(cz + 1, g.n[2] - 1);
+    int rb[9], re[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int ax = cx + k / 3 - 1, ay = cy + k % 3 - 1;
+        const bool ok = ax >= 0 && ax < g.n[0] && ay >= 0 && ay < g.n[1];
+        const uint32_t k0 = ok ? ((uint32_t)ax * g.n[1] + ay) * g.n[2] : 0u;
+        rb[k] = A.cell_start[k0 + zl];
+        re[k] = ok ? A.cell_start[k0 + zh + 1] : rb[k];
     }
-    A.hn_out[s] = cnt;
-    A.fx[s] = fx; A.fy[s] = fy; A.fz[s] = fz;
-    A.tx[s] = tx; A.ty[s] = ty; A.tz[s] = tz;
+    constexpr int kHits = 32;          // >= max_contacts (<= 32)
+    int hits[kHits];
+    int nh = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        for (int j0 = rb[k]; j0 < re[k]; j0 += 4) {
+            R r2[4], rs[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = min(j0 + t, re[k] - 1);
+                r2[t] = dist2<3, R>(xi - A.x[j], yi - A.y[j], zi - A.z[j]);
+                rs[t] = add_rn(ri, A.rad[j]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = j0 + t;
+                if (j < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != s) {
+                    if (nh < kHits) hits[nh] = j;
+                    ++nh;
+                }
+            }
+        }
+    }
+    const R ui = A.u[s], vi = A.v[s], wi = A.w[s], mi = A.m[s];
+    const R owx = mul_rn(ri, A.wx[s]), owy = mul_rn(ri, A.wy[s]), owz = mul_rn(ri, A.wz[s]);   // R_i w_i
+    const int nold = A.hn_in[s];
+    R fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    int cnt = 0;
+    for (int h = 0; h < min(nh, kHits); ++h)
+        dem_contact<R>(C, A, s, hits[h], xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, fx, fy, fz, tx, ty, tz, cnt);
+    if (nh > kHits) cnt = nh;          // more contacts than can ever be stored: reported as overflow below
+    dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
 }
 
 // semi-implicit Euler for spheres: tag 0 only
@@ -171,7 +246,10 @@ pst_status launch_dem(pst_ctx* ctx) {
     A.flags = ctx->d_flags;
     A.stride = ctx->capacity + 2 * ctx->ghost_cap;
     A.n = (int)ctx->n;
-    PST_LAUNCH(ctx, (k_dem_forces<R, MORTON>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
+    if (MORTON || pst_option(ctx, "dem_kernel", 1) == 0)
+        PST_LAUNCH(ctx, (k_dem_forces_generic<R, MORTON>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
+    else
+        PST_LAUNCH(ctx, (k_dem_forces<R>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
     for (PstArray* a : {hn, hid, hx, hy, hz}) a->cur = d;
     return PST_OK;
 }
