@@ -63,6 +63,9 @@ unsafe extern "C" {
     pub fn pst_array(ctx: *mut pst_ctx, name: *const c_char, dev_ptr: *mut *mut c_void, n: *mut usize, dtype: *mut c_int, rows: *mut c_int) -> pst_status;
     pub fn pst_upload(ctx: *mut pst_ctx, name: *const c_char, host: *const c_void, n: usize) -> pst_status;
     pub fn pst_download(ctx: *mut pst_ctx, name: *const c_char, host: *mut c_void, n: usize) -> pst_status;
+    pub fn pst_upload_async(ctx: *mut pst_ctx, name: *const c_char, host: *const c_void, n: usize) -> pst_status;
+    pub fn pst_download_async(ctx: *mut pst_ctx, name: *const c_char, host: *mut c_void, n: usize) -> pst_status;
+    pub fn pst_wait_transfers(ctx: *mut pst_ctx) -> pst_status;
     pub fn pst_host_alloc(bytes: usize) -> *mut c_void;
     pub fn pst_host_free(p: *mut c_void);
     pub fn pst_build_neighbours(ctx: *mut pst_ctx) -> pst_status;
