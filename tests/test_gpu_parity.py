@@ -446,3 +446,57 @@ def test_dem_1m_properties():
     for k in f:
         tot = f[k].sum(); scale = np.abs(f[k]).sum()
         assert abs(tot) <= 1e-10 * scale
+
+
+# ------------------------------------------------------------------------------------------------
+# snapshot I/O: a run split by a checkpoint equals the unsplit run bit for bit (incl. contact history)
+# ------------------------------------------------------------------------------------------------
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    from prestige_b200 import io as pio
+    b = synth.dem_column_3d(8).shuffled()
+    with _ctx(b, np.float64) as ctx:
+        ctx.step(2e-6, 40)
+        ref = {k: ctx.download(k) for k in ("x", "u", "wz", "hist_n", "hist_x")}
+    with _ctx(b, np.float64) as ctx:
+        ctx.step(2e-6, 25)
+        pio.save_checkpoint(ctx, str(tmp_path / "ck.npz"), extra={"t": 25 * 2e-6})
+        pio.write_csv(ctx, str(tmp_path / "s.csv"))
+        pio.write_vtk(ctx, str(tmp_path / "s.vtk"))
+    with pb.context_for_block(b) as ctx:
+        ctx.set_params(**b.params)
+        extra = pio.load_checkpoint(ctx, str(tmp_path / "ck.npz"))
+        assert abs(float(extra["t"]) - 25 * 2e-6) < 1e-18
+        ctx.step(2e-6, 15)
+        got = {k: ctx.download(k) for k in ref}
+    for k in ("x", "u", "wz", "hist_n"):
+        assert np.array_equal(got[k], ref[k]), k
+    # slot order may differ after the reload (history is a keyed set), the multiset of values must not
+    assert np.array_equal(np.sort(np.abs(got["hist_x"]).ravel()), np.sort(np.abs(ref["hist_x"]).ravel()))
+    txt = open(tmp_path / "s.vtk").read()
+    assert txt.startswith("# vtk DataFile") and f"POINTS {b.n} double" in txt and "VECTORS velocity" in txt
+    assert open(tmp_path / "s.csv").readline().startswith("x,y,z,u,v,w")
+
+
+def test_golden_vectors_on_gpu():
+    """The committed fixtures (tests/golden/, made from the oracle) against the CUDA path."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "wcsph3d_small.npz"))
+    b = synth.wcsph_block_3d(9, 8, 7).shuffled()
+    got, pairs = _wcsph_gpu(b, np.float64)
+    assert np.array_equal(pairs, z["pairs"])
+    for k in ("p", "au", "av", "aw", "arho"):
+        assert_close(got[k], z[k], f"golden {k}")
+    z = np.load(os.path.join(gold, "wcsph2d_small.npz"))
+    c = synth.wcsph_dambreak_2d(dx=0.05).shuffled()
+    got, _ = _wcsph_gpu(c, np.float64)
+    for k in ("p", "au", "av", "arho"):
+        assert_close(got[k], z[k], f"golden 2d {k}")
+    z = np.load(os.path.join(gold, "dem3d_small.npz"))
+    d = synth.dem_column_3d(6).shuffled()
+    with _ctx(d, np.float64) as ctx:
+        ctx.build_neighbours()
+        ctx.apply(["dem_contact"]); ctx.apply(["dem_contact"])
+        for k in ("fx", "fy", "fz", "tx", "ty", "tz"):
+            assert_close(ctx.download(k), z[k], f"golden dem {k}")
+        assert np.array_equal(ctx.download("hist_n"), z["hist_n"])
