@@ -7,6 +7,7 @@
 #include <cmath>
 #include <algorithm>
 #include <set>
+#include <vector>
 
 #include "pst_internal.h"
 
@@ -226,14 +227,16 @@ static pst_status ring_acquire(pst_ctx* ctx, cudaStream_t user, bool upload, int
     int k;
     if (upload) { k = ctx->ring_next_up; ctx->ring_next_up = (k + 1) % kUp; }
     else { k = kUp + ctx->ring_next_down; ctx->ring_next_down = (ctx->ring_next_down + 1) % kDown; }
-    if (!ctx->ring[k]) {
+    if (!ctx->ring[0]) {   // first asynchronous transfer: allocate the whole ring once (no cudaMalloc on the hot path later)
         const size_t bytes = (ctx->capacity + 2 * ctx->ghost_cap) * 8;
-        if (cudaMalloc((void**)&ctx->ring[k], bytes) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "staging ring buffer (%zu bytes)", bytes);
-        PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_free[k], cudaEventDisableTiming));
-        PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_ready[k], cudaEventDisableTiming));
-    } else {
-        PST_CUDA(ctx, cudaStreamWaitEvent(user, ctx->ring_free[k], 0));
+        for (int r = 0; r < pst_ctx::kRing; ++r) {
+            if (cudaMalloc((void**)&ctx->ring[r], bytes) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "staging ring (%d x %zu bytes)", pst_ctx::kRing, bytes);
+            PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_free[r], cudaEventDisableTiming));
+            PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_ready[r], cudaEventDisableTiming));
+            PST_CUDA(ctx, cudaEventRecord(ctx->ring_free[r], ctx->stream));
+        }
     }
+    PST_CUDA(ctx, cudaStreamWaitEvent(user, ctx->ring_free[k], 0));
     *idx = k;
     return PST_OK;
 }
@@ -351,8 +354,23 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     PstArray* a = pst_find(ctx, name);
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles (pst_set_count first)", name, n, (unsigned long long)ctx->n);
-    if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (a->name == "id") {
+        // Restoring a checkpoint in DEVICE order: right after pst_set_count (identity order) the caller may declare
+        // which stable id sits in which slot.  Must be a permutation of 0..n-1; from here on host arrays are id-ordered.
+        if (ctx->ordered) return pst_fail(ctx, PST_ESTATE, "'id' can only be set right after pst_set_count");
+        const uint32_t* ids = (const uint32_t*)host;
+        std::vector<bool> seen(n, false);
+        for (size_t k = 0; k < n; ++k) {
+            if (ids[k] >= n || seen[ids[k]]) return pst_fail(ctx, PST_EINVAL, "'id' must be a permutation of 0..n-1");
+            seen[ids[k]] = true;
+        }
+        PST_CUDA(ctx, cudaMemcpyAsync(pst_ptr<char>(ctx, a), host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->ordered = true;
+        ctx->nbrs_valid = false;
+        return PST_OK;
+    }
     for (int r = 0; r < a->rows; ++r) {
         const char* src = (const char*)host + (size_t)r * n * a->esize;
         if (!ctx->ordered) {

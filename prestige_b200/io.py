@@ -20,9 +20,14 @@ def state_names(ctx) -> list:
 
 
 def save_checkpoint(ctx, path: str, extra: dict | None = None) -> None:
-    """Every persistent array (incl. contact history) in id order -> one .npz.  Reloading reproduces the run bit for bit."""
+    """Every persistent array (incl. contact history) plus the DEVICE ORDER -> one .npz.
+
+    Arrays are stored in id order together with `__order` (the stable id held by each device slot).  Restoring the
+    device order matters for bit-exact resumption: the radix sort is stable, so the order inside a cell -- and with
+    it the floating-point summation order of every pair loop -- depends on the order before the sort."""
     data = {k: ctx.download(k) for k in state_names(ctx)}
     data["__n"] = np.array([ctx.n], np.int64)
+    data["__order"] = ctx.download("id")
     for k, v in (extra or {}).items():
         data["__extra_" + k] = np.asarray(v)
     np.savez(path, **data)
@@ -32,13 +37,15 @@ def load_checkpoint(ctx, path: str) -> dict:
     """Restore a checkpoint into a context created with the same configuration.  Returns the `extra` dict."""
     z = np.load(path)
     n = int(z["__n"][0])
-    ctx.set_count(n)
+    order = z["__order"].astype(np.uint32)
+    ctx.set_count(n)                                  # identity order: uploads land slot by slot
     for k in z.files:
         if k.startswith("__"):
             continue
         if not ctx.has_array(k):
             raise KeyError(f"checkpoint array '{k}' does not exist in this context")
-        ctx.upload(k, z[k])
+        ctx.upload(k, np.ascontiguousarray(z[k][..., order]))     # id order -> saved device order
+    ctx.upload("id", order)                           # declare the ids; host arrays are id-ordered again from here on
     return {k[len("__extra_"):]: z[k] for k in z.files if k.startswith("__extra_")}
 
 

@@ -468,10 +468,8 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
         assert abs(float(extra["t"]) - 25 * 2e-6) < 1e-18
         ctx.step(2e-6, 15)
         got = {k: ctx.download(k) for k in ref}
-    for k in ("x", "u", "wz", "hist_n"):
+    for k in ("x", "u", "wz", "hist_n", "hist_x"):
         assert np.array_equal(got[k], ref[k]), k
-    # slot order may differ after the reload (history is a keyed set), the multiset of values must not
-    assert np.array_equal(np.sort(np.abs(got["hist_x"]).ravel()), np.sort(np.abs(ref["hist_x"]).ravel()))
     txt = open(tmp_path / "s.vtk").read()
     assert txt.startswith("# vtk DataFile") and f"POINTS {b.n} double" in txt and "VECTORS velocity" in txt
     assert open(tmp_path / "s.csv").readline().startswith("x,y,z,u,v,w")
