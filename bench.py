@@ -250,8 +250,8 @@ def main():
         run_reference(args, rank)
         return
 
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     import prestige_b200 as pb
@@ -355,6 +355,8 @@ def main():
         def e2e_step():
             # the public asynchronous path: H2D of this step's state and D2H of the previous step's rates ride the two
             # copy engines (PCIe is full duplex) while the compute stream works; every byte still crosses every step
+            if world > 1:
+                ctx.set_count(n)                 # distributed mode: host arrays are in device order, so restart from the host order
             for k in ins:
                 ctx.upload_async(k, hin[k].ctypes.data)
             step()

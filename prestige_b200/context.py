@@ -149,8 +149,16 @@ class Context:
                 self.upload(k, v)
 
     # -- the hot path -----------------------------------------------------------------------
+    def refresh_count(self) -> int:
+        """Owned-particle count as the library sees it (changes when particles migrate between ranks)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.pst_get_count(self._h, C.byref(a), C.byref(b)))
+        self.n = a.value
+        return self.n
+
     def build_neighbours(self):
         self._ck(self._lib.pst_build_neighbours(self._h))
+        self.refresh_count()
 
     def apply(self, names):
         arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
@@ -166,6 +174,7 @@ class Context:
 
     def step(self, dt: float, n_steps: int = 1):
         self._ck(self._lib.pst_step(self._h, dt, n_steps))
+        self.refresh_count()
 
     def integrate(self, dt: float):
         self._ck(self._lib.pst_integrate(self._h, dt))

@@ -250,7 +250,7 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
     if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
-    if (!ctx->ordered || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / history rows: plain path
+    if (!ctx->ordered || ctx->comm || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / distributed mode / history rows: plain path
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     int k = 0;
     PST_TRY(ring_acquire(ctx, ctx->h2d_stream, true, &k));
@@ -273,7 +273,7 @@ pst_status pst_download_async(pst_ctx* ctx, const char* name, void* host, size_t
     PstArray* a = pst_find(ctx, name);
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "download '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
-    if (!ctx->ordered || a->rows != 1 || a->name == "id") return pst_download(ctx, name, host, n);
+    if (!ctx->ordered || ctx->comm || a->rows != 1 || a->name == "id") return pst_download(ctx, name, host, n);
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     int k = 0;
     PST_TRY(ring_acquire(ctx, ctx->stream, false, &k));
@@ -358,6 +358,11 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     if (a->name == "id") {
         // Restoring a checkpoint in DEVICE order: right after pst_set_count (identity order) the caller may declare
         // which stable id sits in which slot.  Must be a permutation of 0..n-1; from here on host arrays are id-ordered.
+        if (ctx->comm) {   // distributed mode: ids are global labels, transfers are in device order
+            PST_CUDA(ctx, cudaMemcpyAsync(pst_ptr<char>(ctx, a), host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return PST_OK;
+        }
         if (ctx->ordered) return pst_fail(ctx, PST_ESTATE, "'id' can only be set right after pst_set_count");
         const uint32_t* ids = (const uint32_t*)host;
         std::vector<bool> seen(n, false);
@@ -373,7 +378,7 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     }
     for (int r = 0; r < a->rows; ++r) {
         const char* src = (const char*)host + (size_t)r * n * a->esize;
-        if (!ctx->ordered) {
+        if (!ctx->ordered || ctx->comm) {   // identity order, or distributed mode (host arrays in device order)
             PST_CUDA(ctx, cudaMemcpyAsync(pst_ptr<char>(ctx, a, r), src, n * a->esize, cudaMemcpyHostToDevice, ctx->stream));
         } else {
             PST_CUDA(ctx, cudaMemcpyAsync(ctx->stage, src, n * a->esize, cudaMemcpyHostToDevice, ctx->stream));
@@ -393,7 +398,7 @@ pst_status pst_download(pst_ctx* ctx, const char* name, void* host, size_t n) {
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     for (int r = 0; r < a->rows; ++r) {
         char* dst = (char*)host + (size_t)r * n * a->esize;
-        if (!ctx->ordered || a->name == "id") {
+        if (!ctx->ordered || ctx->comm || a->name == "id") {
             PST_CUDA(ctx, cudaMemcpyAsync(dst, pst_ptr<char>(ctx, a, r), n * a->esize, cudaMemcpyDeviceToHost, ctx->stream));
         } else {
             PST_TRY(pst_reorder_download(ctx, a, r, n));

@@ -143,8 +143,8 @@ extern "C" pst_status pst_comm_init(pst_ctx* ctx, const void* id_bytes, int rank
     PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     PST_CUDA(ctx, cudaFree(ctx->cell_start));
     ctx->cell_start = nullptr;
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)g.ncells + 1) * 4));
-    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)g.ncells + 1) * 4, ctx->stream));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)g.ncells + 4) * 4));
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)g.ncells + 4) * 4, ctx->stream));
     PstComm* c = new PstComm();
     c->rank = rank; c->nranks = n_ranks;
     const size_t layer = (size_t)g.n[1] * g.n[2] + 1;
@@ -170,6 +170,68 @@ pst_status pst_comm_destroy(pst_ctx* ctx) {
     if (c->h_counts) cudaFreeHost(c->h_counts);
     delete c;
     ctx->comm = nullptr;
+    return PST_OK;
+}
+
+void pst_comm_neighbours(pst_ctx* ctx, int* has_left, int* has_right) {
+    *has_left = ctx->comm && ctx->comm->rank > 0;
+    *has_right = ctx->comm && ctx->comm->rank + 1 < ctx->comm->nranks;
+}
+
+// Particle migration.  build_pass(mig) has sorted the leavers behind the stayers: [n_stay, n_stay + nL) go left,
+// [n_stay + nL, n) go right, as contiguous ranges of EVERY persistent array (state, id, tag, contact-history rows), so
+// they are sent as they are.  Arrivals are received into the free halves of the double buffers and appended after the
+// stayers; the caller re-sorts if anything arrived.  History rows travel with their particle (partner ids must then
+// be globally unique: upload a global "id" array in distributed runs).
+pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
+    *arrivals = 0;
+    PstComm* c = ctx->comm;
+    NcclApi* api = nccl_api();
+    const int left = c->rank > 0 ? c->rank - 1 : -1, right = c->rank + 1 < c->nranks ? c->rank + 1 : -1;
+    const size_t nc = ctx->grid.ncells;
+    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 4, ctx->cell_start + nc, 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n_stay = c->h_counts[4], nL = c->h_counts[5] - c->h_counts[4], nR = c->h_counts[6] - c->h_counts[5];
+    c->h_counts[0] = nL; c->h_counts[1] = nR; c->h_counts[2] = c->h_counts[3] = 0;
+    PST_CUDA(ctx, cudaMemcpyAsync(c->d_counts, c->h_counts, 4 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PST_NCCL(ctx, api->GroupStart());
+    if (left >= 0) { PST_NCCL(ctx, api->Send(c->d_counts + 0, 4, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 2, 4, ncclInt8, left, c->comm, ctx->stream)); }
+    if (right >= 0) { PST_NCCL(ctx, api->Send(c->d_counts + 1, 4, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 3, 4, ncclInt8, right, c->comm, ctx->stream)); }
+    PST_NCCL(ctx, api->GroupEnd());
+    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 2, c->d_counts + 2, 2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int aL = left >= 0 ? c->h_counts[2] : 0, aR = right >= 0 ? c->h_counts[3] : 0;
+    if ((uint64_t)n_stay + aL + aR > ctx->capacity)
+        return pst_fail(ctx, PST_ENOMEM, "migration: %d stayers + %d arrivals exceed capacity %llu", n_stay, aL + aR, (unsigned long long)ctx->capacity);
+    if (nL + nR + aL + aR > 0) {
+        PST_NCCL(ctx, api->GroupStart());
+        for (auto& a : ctx->arrays) {
+            if (!(a.flags & PST_ARRAY_PERSISTENT)) continue;
+            const size_t es = a.esize;
+            for (int r = 0; r < a.rows; ++r) {
+                char* cur = pst_ptr<char>(ctx, &a, r, a.cur);
+                char* alt = pst_ptr<char>(ctx, &a, r, 1 - a.cur);
+                if (left >= 0) {
+                    if (nL > 0) PST_NCCL(ctx, api->Send(cur + (size_t)n_stay * es, (size_t)nL * es, ncclInt8, left, c->comm, ctx->stream));
+                    if (aL > 0) PST_NCCL(ctx, api->Recv(alt, (size_t)aL * es, ncclInt8, left, c->comm, ctx->stream));
+                }
+                if (right >= 0) {
+                    if (nR > 0) PST_NCCL(ctx, api->Send(cur + (size_t)(n_stay + nL) * es, (size_t)nR * es, ncclInt8, right, c->comm, ctx->stream));
+                    if (aR > 0) PST_NCCL(ctx, api->Recv(alt + (size_t)aL * es, (size_t)aR * es, ncclInt8, right, c->comm, ctx->stream));
+                }
+            }
+        }
+        PST_NCCL(ctx, api->GroupEnd());
+        if (aL + aR > 0)
+            for (auto& a : ctx->arrays) {
+                if (!(a.flags & PST_ARRAY_PERSISTENT)) continue;
+                for (int r = 0; r < a.rows; ++r)
+                    PST_CUDA(ctx, cudaMemcpyAsync(pst_ptr<char>(ctx, &a, r, a.cur) + (size_t)n_stay * a.esize, pst_ptr<char>(ctx, &a, r, 1 - a.cur),
+                                                  (size_t)(aL + aR) * a.esize, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+    }
+    ctx->n = (uint64_t)(n_stay + aL + aR);
+    *arrivals = aL + aR;
     return PST_OK;
 }
 

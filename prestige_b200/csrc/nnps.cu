@@ -22,16 +22,23 @@ __global__ void k_iota(uint32_t* __restrict__ id, int n) {
     if (s < n) id[s] = (uint32_t)s;
 }
 
+// mig_l / mig_r (slab decomposition only): an owned particle that has left the slab through the left / right face gets
+// the sentinel key ncells / ncells + 1, so the sort parks the leavers behind the stayers as two contiguous ranges that
+// can be sent to the neighbour rank as they are.
 template <class R, int DIM, bool MORTON>
 __global__ void __launch_bounds__(kThreads) k_keys(GridDev<R> g, int n, const R* __restrict__ x, const R* __restrict__ y,
                                                    const R* __restrict__ z, uint32_t* __restrict__ keys,
-                                                   uint32_t* __restrict__ vals) {
+                                                   uint32_t* __restrict__ vals, uint32_t ncells, int mig_l, int mig_r) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const int cx = cell_coord<R>(x[s], g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cxu = (int)floor((x[s] - g.lo[0]) * g.inv_cell);
+    const int cx = min(max(cxu, g.cx_lo), g.cx_hi);
     const int cy = cell_coord<R>(y[s], g.lo[1], g.inv_cell, 0, g.n[1] - 1);
     const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
-    keys[s] = cell_key<DIM, MORTON>(g, cx, cy, cz);
+    uint32_t key = cell_key<DIM, MORTON>(g, cx, cy, cz);
+    if (mig_l && cxu < g.cx_lo) key = ncells;
+    else if (mig_r && cxu > g.cx_hi) key = ncells + 1u;
+    keys[s] = key;
     vals[s] = (uint32_t)s;
 }
 
@@ -137,10 +144,11 @@ __global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, in
 }
 
 template <class R, int DIM, bool MORTON>
-pst_status launch_keys(pst_ctx* ctx) {
+pst_status launch_keys(pst_ctx* ctx, int mig_l, int mig_r) {
     const int n = (int)ctx->n;
     PST_LAUNCH(ctx, (k_keys<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n,
-               pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, ctx->keys_in, ctx->vals_in);
+               pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, ctx->keys_in, ctx->vals_in,
+               ctx->grid.ncells, mig_l, mig_r);
     return PST_OK;
 }
 
@@ -180,8 +188,8 @@ pst_status pst_nnps_alloc(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->keys_out, cap * 4));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->vals_in, cap * 4));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->vals_out, cap * 4));
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)ctx->grid.ncells + 1) * 4));
-    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)ctx->grid.ncells + 1) * 4, ctx->stream));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)ctx->grid.ncells + 4) * 4));
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)ctx->grid.ncells + 4) * 4, ctx->stream));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->stage, cap * 8));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_flags, 8 * sizeof(int32_t)));
     PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
@@ -203,16 +211,21 @@ pst_status pst_iota_ids(pst_ctx* ctx) {
     return PST_OK;
 }
 
-pst_status pst_nnps_build(pst_ctx* ctx) {
-    if (!pst_find(ctx, "x")) return pst_fail(ctx, PST_ESTATE, "context has no position arrays (physics = PST_PHYS_NONE)");
+// one pass of keys -> sort -> cell table -> permute (+ history remap).  With mig_l / mig_r the leavers end up behind the
+// stayers: cell_start[ncells] = n_stay, cell_start[ncells + 1] = n_stay + n_left, cell_start[ncells + 2] = n.
+static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     const int n = (int)ctx->n;
+    const bool mig = mig_l || mig_r;
+    const uint32_t nkeys = ctx->grid.ncells + (mig ? 2u : 0u);
+    int key_bits = ctx->grid.key_bits;
+    while (mig && (1ull << key_bits) < (unsigned long long)nkeys) ++key_bits;
     ctx->n_ghost_l = ctx->n_ghost_r = 0;
     if (n > 0) {
-        PST_TRY(PST_DISPATCH(ctx, launch_keys, ctx));
+        PST_TRY(PST_DISPATCH(ctx, launch_keys, ctx, mig_l, mig_r));
         size_t tmp = ctx->sort_tmp_bytes;
         PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tmp, ctx->keys_in, ctx->keys_out, ctx->vals_in, ctx->vals_out,
-                                                      n, 0, ctx->grid.key_bits, ctx->stream));
-        ctx->launches += (ctx->grid.key_bits + 7) / 8 + 2;  // CUB onesweep: histogram + scan + one pass per 8 bits
+                                                      n, 0, key_bits, ctx->stream));
+        ctx->launches += (key_bits + 7) / 8 + 2;  // CUB onesweep: histogram + scan + one pass per 8 bits
     }
     // occupied-cell count of the PREVIOUS build (read back asynchronously; the very first build waits once)
     if (ctx->stats_pending) {
@@ -221,7 +234,7 @@ pst_status pst_nnps_build(pst_ctx* ctx) {
         if (ctx->h_counters[2] > 0) ctx->params["_ppc"] = (double)ctx->h_counters[3] / (double)ctx->h_counters[2];
     }
     PST_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(unsigned long long), ctx->stream));
-    PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, ctx->grid.ncells, ctx->keys_out, ctx->cell_start, ctx->d_counters);
+    PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, nkeys, ctx->keys_out, ctx->cell_start, ctx->d_counters);
     PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaEventRecord(ctx->ev_stats, ctx->stream));
     ctx->h_counters[3] = (unsigned long long)n;
@@ -255,6 +268,20 @@ pst_status pst_nnps_build(pst_ctx* ctx) {
     ctx->ordered = true;
     ctx->nbrs_valid = true;
     ctx->eos_valid = false;
+    return PST_OK;
+}
+
+pst_status pst_nnps_build(pst_ctx* ctx) {
+    if (!pst_find(ctx, "x")) return pst_fail(ctx, PST_ESTATE, "context has no position arrays (physics = PST_PHYS_NONE)");
+    if (!ctx->comm) return build_pass(ctx, 0, 0);
+    // slab decomposition: park the particles that left the slab behind the stayers, hand them to the neighbour ranks,
+    // take theirs in, and re-sort only if somebody arrived
+    int mig_l = 0, mig_r = 0;
+    pst_comm_neighbours(ctx, &mig_l, &mig_r);
+    PST_TRY(build_pass(ctx, mig_l, mig_r));
+    int arrivals = 0;
+    PST_TRY(pst_migrate(ctx, &arrivals));
+    if (arrivals > 0) PST_TRY(build_pass(ctx, 0, 0));
     return PST_OK;
 }
 

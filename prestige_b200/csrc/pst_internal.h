@@ -128,6 +128,8 @@ pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu
 pst_status pst_dem_integrate(pst_ctx* ctx, double dt);
 pst_status pst_comm_destroy(pst_ctx* ctx);                                // halo.cu
+void pst_comm_neighbours(pst_ctx* ctx, int* has_left, int* has_right);
+pst_status pst_migrate(pst_ctx* ctx, int* arrivals);   // after a build pass with sentinel keys: ship leavers, append arrivals
 
 // ---------------------------------------------------------------------------------------------
 // device side

@@ -19,45 +19,84 @@ from oracle import oracle as orc                # noqa: E402
 from util import rel_err                        # noqa: E402
 
 
-def main():
-    out = sys.argv[1]
-    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    whole = synth.wcsph_block_3d(60, 24, 20)
+def _slab_context(whole, rank, world, lr, extra_cap=0):
     cell = whole.cell_size
     n_layers = int(np.ceil((whole.hi[0] - whole.lo[0]) / cell))
     first, k = decomp.split_layers(n_layers, world)[rank]
     lo, hi = whole.lo[0] + first * cell, whole.lo[0] + (first + k) * cell
     own = decomp.owner_mask(whole.arrays["x"], lo, hi, rank == 0, rank == world - 1)
-    mine = {c: np.ascontiguousarray(v[own]) for c, v in whole.arrays.items()}
     n = int(own.sum())
+    ctx = pb.Context(dim=3, lo=(lo, whole.lo[1], whole.lo[2]), hi=(hi, whole.hi[1], whole.hi[2]), cell_size=cell, capacity=n + extra_cap + 16,
+                     physics="wcsph", device=lr, ghost_capacity=decomp.ghost_capacity(24, 20, cell, whole.meta["dx"]))
+    uid = [pb.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    ctx.set_count(n)
+    ctx.set_params(**whole.params)
+    for c, v in whole.arrays.items():
+        ctx.upload(c, np.ascontiguousarray(v[own]))
+    ctx.upload("id", np.nonzero(own)[0].astype(np.uint32))      # distributed mode: global labels, device-order transfers
+    return ctx, own
+
+
+def halo_parity(out, rank, world, lr):
+    whole = synth.wcsph_block_3d(60, 24, 20)
     res = {}
-    for variant in (1, 0):
-        ctx = pb.Context(dim=3, lo=(lo, whole.lo[1], whole.lo[2]), hi=(hi, whole.hi[1], whole.hi[2]), cell_size=cell, capacity=n + 16,
-                         physics="wcsph", device=lr, ghost_capacity=decomp.ghost_capacity(24, 20, cell, whole.meta["dx"]))
-        uid = [pb.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
+    ref = orc.wcsph(3, whole.params, whole.arrays, grid=orc.make_grid(3, whole.lo, whole.hi, whole.cell_size))
+    for variant in (2, 1, 0):
+        ctx, own = _slab_context(whole, rank, world, lr)
         ctx.set_option("force_kernel", variant)
-        ctx.set_count(n)
-        ctx.set_params(**whole.params)
-        for c, v in mine.items():
-            ctx.upload(c, v)
         for rep in range(2):                     # second pass: identity re-sort + fresh halo
             ctx.build_neighbours()
             ctx.halo_exchange()
             ctx.apply(["tait_eos", "continuity", "momentum"])
-        got = {c: ctx.download(c) for c in ("au", "av", "aw", "arho", "p")}
-        ghosts = (ctx.stat("n_ghost_l"), ctx.stat("n_ghost_r"))
+        gid = ctx.download("id").astype(np.int64)
+        assert np.array_equal(np.sort(gid), np.nonzero(own)[0])
+        res[variant] = {c: rel_err(ctx.download(c), ref[c][gid]) for c in ("au", "av", "aw", "arho", "p")}
+        res[variant]["ghosts"] = (ctx.stat("n_ghost_l"), ctx.stat("n_ghost_r"))
+        n = ctx.n
         ctx.close()
-        ref = orc.wcsph(3, whole.params, whole.arrays, grid=orc.make_grid(3, whole.lo, whole.hi, cell))
-        res[variant] = {c: rel_err(got[c], ref[c][own]) for c in got}
-        res[variant]["ghosts"] = ghosts
     tot = torch.tensor([n], device="cuda")
     dist.all_reduce(tot)
     with open(os.path.join(out, f"rank{rank}.json"), "w") as f:
         json.dump({"rank": rank, "world": world, "n": n, "n_total": int(tot[0]), "n_whole": whole.n, "err": {str(k): v for k, v in res.items()}}, f)
+
+
+def migration(out, rank, world, lr):
+    """A block drifting along +x through the slab faces: pst_step on `world` ranks (re-sort, MIGRATION, halo, forces,
+    integrate every step) against the same steps on one GPU; particles are matched by global id."""
+    whole = synth.wcsph_block_3d(48, 24, 20)
+    whole.params["gz"] = 0.0
+    whole.arrays["u"] = whole.arrays["u"] + 3.0
+    dt, steps = 4e-5, 120                        # drift 3 m/s * 4.8 ms = 1.2 cells
+    ctx, own = _slab_context(whole, rank, world, lr, extra_cap=whole.n // 2)
+    n0 = ctx.n
+    ctx.step(dt, steps)
+    ctx.sync()
+    cnt = ctx.refresh_count()
+    gid = ctx.download("id").astype(np.int64)
+    got = {c: ctx.download(c) for c in ("x", "y", "z", "u", "rho")}
+    ctx.close()
+    # single-GPU truth on this rank's device
+    with pb.context_for_block(whole, device=lr) as one:
+        one.load_block(whole)
+        one.step(dt, steps)
+        ref = {c: one.download(c) for c in got}
+    err = {c: float(np.max(np.abs(got[c] - ref[c][gid]) / max(np.abs(ref[c]).max(), 1e-300))) if len(gid) else 0.0 for c in got}
+    allg = [None] * world
+    dist.all_gather_object(allg, gid.tolist())
+    flat = np.sort(np.concatenate([np.array(g, dtype=np.int64) for g in allg]))
+    with open(os.path.join(out, f"rank{rank}.json"), "w") as f:
+        json.dump({"rank": rank, "world": world, "n0": n0, "n1": int(cnt), "moved": int(n0 != cnt), "err": err,
+                   "all_ids_once": bool(np.array_equal(flat, np.arange(whole.n)))}, f)
+
+
+def main():
+    out, mode = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "halo")
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    (halo_parity if mode == "halo" else migration)(out, rank, world, lr)
     dist.barrier(device_ids=[lr])
     dist.destroy_process_group()
 
