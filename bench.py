@@ -76,6 +76,8 @@ def make_block(workload: str, rank: int = 0, world: int = 1):
         return b, (lo_x, hi_x)
     if workload == "dem3d_1m":
         return synth.dem_column_3d(100), None
+    if workload == "dem3d_8m":
+        return synth.dem_column_3d(200), None
     if workload == "wcsph2d_20k":
         return synth.wcsph_dambreak_2d(dx=0.01), None
     if workload.startswith("wcsph3d_"):     # e.g. wcsph3d_1m: cubes for quick runs
@@ -142,7 +144,7 @@ def cpu_sample_block(workload: str):
     from prestige_b200 import synth
     if workload.startswith("wcsph3d"):
         return synth.wcsph_block_3d(100, 100, 100), "first 100x100x100 lattice planes (1.0 M particles) of the same generator"
-    if workload == "dem3d_1m":
+    if workload.startswith("dem3d"):
         return synth.dem_column_3d(64), "64^3 spheres + floor (0.27 M particles) of the same generator"
     return synth.wcsph_dambreak_2d(dx=0.01), "the full 2D dam break (23 k particles)"
 

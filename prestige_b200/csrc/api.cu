@@ -318,6 +318,7 @@ pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
     ctx->ordered = false;
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;
+    ctx->hist_lag = false;
     PST_TRY(pst_iota_ids(ctx));
     if (PstArray* hn = pst_find(ctx, "hist_n")) {
         const size_t stride = ctx->capacity + 2 * ctx->ghost_cap;
@@ -355,6 +356,7 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles (pst_set_count first)", name, n, (unsigned long long)ctx->n);
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (a->name.rfind("hist_", 0) == 0) PST_TRY(pst_resolve_history(ctx));
     if (a->name == "id") {
         // Restoring a checkpoint in DEVICE order: right after pst_set_count (identity order) the caller may declare
         // which stable id sits in which slot.  Must be a permutation of 0..n-1; from here on host arrays are id-ordered.
@@ -396,6 +398,7 @@ pst_status pst_download(pst_ctx* ctx, const char* name, void* host, size_t n) {
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "download '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (a->name.rfind("hist_", 0) == 0) PST_TRY(pst_resolve_history(ctx));
     for (int r = 0; r < a->rows; ++r) {
         char* dst = (char*)host + (size_t)r * n * a->esize;
         if (!ctx->ordered || ctx->comm || a->name == "id") {
@@ -508,6 +511,7 @@ pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value) {
         if (!hn) return pst_fail(ctx, PST_EINVAL, "no contact history in this context");
         std::vector<int32_t> h(ctx->n);
         PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+        PST_TRY(pst_resolve_history(ctx));
         PST_CUDA(ctx, cudaMemcpyAsync(h.data(), pst_ptr<int32_t>(ctx, hn), ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         double t = 0;

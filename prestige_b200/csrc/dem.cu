@@ -27,6 +27,7 @@ struct DemArgs {
     const R *x, *y, *z, *u, *v, *w, *wx, *wy, *wz, *rad, *m;
     const uint32_t* id;
     const int32_t* hn_in; const uint32_t* hid_in; const R *hx_in, *hy_in, *hz_in;
+    const uint32_t* hperm;   // deferred history remap: old row of particle s is hperm[s] (nullptr: rows already in place)
     int32_t* hn_out; uint32_t* hid_out; R *hx_out, *hy_out, *hz_out;
     R *fx, *fy, *fz, *tx, *ty, *tz;
     const int32_t* cell_start;
@@ -38,7 +39,7 @@ struct DemArgs {
 // one contact: normal + tangential law, history lookup by stable partner id, torque.  Shared by both kernels.
 template <class R>
 __device__ __forceinline__ void dem_contact(const DemConst<R>& C, const DemArgs<R>& A, int s, int j, R xi, R yi, R zi, R ui, R vi, R wi, R ri,
-                                            R mi, R owx, R owy, R owz, int nold, R& fx, R& fy, R& fz, R& tx, R& ty, R& tz, int& cnt) {
+                                            R mi, R owx, R owy, R owz, int nold, int hrow, R& fx, R& fy, R& fz, R& tx, R& ty, R& tz, int& cnt) {
     const R dx = xi - A.x[j], dy = yi - A.y[j], dz = zi - A.z[j];
     const R r2 = dist2<3, R>(dx, dy, dz);
     const R rj = A.rad[j];
@@ -72,10 +73,10 @@ __device__ __forceinline__ void dem_contact(const DemConst<R>& C, const DemArgs<
     const uint32_t pid = A.id[j];
     int slot = -1;
     for (int k = 0; k < nold; ++k)
-        if (A.hid_in[(size_t)k * A.stride + s] == pid) slot = k;
+        if (A.hid_in[(size_t)k * A.stride + hrow] == pid) slot = k;
     R hx = 0, hy = 0, hz = 0;
     if (slot >= 0) {
-        const size_t o = (size_t)slot * A.stride + s;
+        const size_t o = (size_t)slot * A.stride + hrow;
         hx = A.hx_in[o]; hy = A.hy_in[o]; hz = A.hz_in[o];
     }
     const R xn = hx * nx + hy * ny + hz * nz;
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
     const R ui = A.u[s], vi = A.v[s], wi = A.w[s];
     const R ri = A.rad[s], mi = A.m[s];
     const R owx = mul_rn(ri, A.wx[s]), owy = mul_rn(ri, A.wy[s]), owz = mul_rn(ri, A.wz[s]);   // R_i w_i
-    const int nold = A.hn_in[s];
+    const int hrow = A.hperm ? (int)A.hperm[s] : s;
+    const int nold = A.hn_in[hrow];
     const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
     const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
     const int cz = cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
             const R r2 = dist2<3, R>(dx, dy, dz);
             const R rs = add_rn(ri, A.rad[j]);
             if (!(r2 < mul_rn(rs, rs)) || !(r2 > (R)0) || j == s) continue;
-            dem_contact<R>(C, A, s, j, xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, fx, fy, fz, tx, ty, tz, cnt);
+            dem_contact<R>(C, A, s, j, xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
         }
     });
     dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
@@ -189,11 +191,12 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces(GridDev<R> g, DemConst<
     }
     const R ui = A.u[s], vi = A.v[s], wi = A.w[s], mi = A.m[s];
     const R owx = mul_rn(ri, A.wx[s]), owy = mul_rn(ri, A.wy[s]), owz = mul_rn(ri, A.wz[s]);   // R_i w_i
-    const int nold = A.hn_in[s];
+    const int hrow = A.hperm ? (int)A.hperm[s] : s;
+    const int nold = A.hn_in[hrow];
     R fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     int cnt = 0;
     for (int h = 0; h < min(nh, kHits); ++h)
-        dem_contact<R>(C, A, s, hits[h], xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, fx, fy, fz, tx, ty, tz, cnt);
+        dem_contact<R>(C, A, s, hits[h], xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
     if (nh > kHits) cnt = nh;          // more contacts than can ever be stored: reported as overflow below
     dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
 }
@@ -242,6 +245,7 @@ pst_status launch_dem(pst_ctx* ctx) {
     A.hx_out = pst_ptr<R>(ctx, hx, 0, d); A.hy_out = pst_ptr<R>(ctx, hy, 0, d); A.hz_out = pst_ptr<R>(ctx, hz, 0, d);
     A.fx = pst_ptr<R>(ctx, "fx"); A.fy = pst_ptr<R>(ctx, "fy"); A.fz = pst_ptr<R>(ctx, "fz");
     A.tx = pst_ptr<R>(ctx, "tx"); A.ty = pst_ptr<R>(ctx, "ty"); A.tz = pst_ptr<R>(ctx, "tz");
+    A.hperm = ctx->hist_lag ? ctx->vals_out : nullptr;
     A.cell_start = ctx->cell_start;
     A.flags = ctx->d_flags;
     A.stride = ctx->capacity + 2 * ctx->ghost_cap;
@@ -251,6 +255,7 @@ pst_status launch_dem(pst_ctx* ctx) {
     else
         PST_LAUNCH(ctx, (k_dem_forces<R>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
     for (PstArray* a : {hn, hid, hx, hy, hz}) a->cur = d;
+    ctx->hist_lag = false;   // the pass wrote every row at its new index
     return PST_OK;
 }
 

@@ -214,6 +214,7 @@ pst_status pst_iota_ids(pst_ctx* ctx) {
 // one pass of keys -> sort -> cell table -> permute (+ history remap).  With mig_l / mig_r the leavers end up behind the
 // stayers: cell_start[ncells] = n_stay, cell_start[ncells + 1] = n_stay + n_left, cell_start[ncells + 2] = n.
 static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
+    PST_TRY(pst_resolve_history(ctx));   // vals_out of the previous sort is about to be overwritten
     const int n = (int)ctx->n;
     const bool mig = mig_l || mig_r;
     const uint32_t nkeys = ctx->grid.ncells + (mig ? 2u : 0u);
@@ -263,12 +264,25 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
             }
         PST_LAUNCH(ctx, k_permute, blocks_for(n), kThreads, 0, L, n, ctx->vals_out);
         for (PstArray* a : moved) a->cur = 1 - a->cur;
-        if (ctx->f64) PST_TRY(launch_remap<double>(ctx)); else PST_TRY(launch_remap<float>(ctx));
+        // Contact history: the remap is DEFERRED -- the next contact pass reads each row through vals_out (new -> old
+        // index) and writes it back in place of a separate 2 x (28 Z + 4) B/particle copy.  Anything else that needs the
+        // rows in the new order (a second re-sort, a download, migration) resolves the lag first.
+        if (pst_find(ctx, "hist_n")) {
+            if (ctx->comm) { if (ctx->f64) PST_TRY(launch_remap<double>(ctx)); else PST_TRY(launch_remap<float>(ctx)); }
+            else ctx->hist_lag = true;
+        }
     }
     ctx->ordered = true;
     ctx->nbrs_valid = true;
     ctx->eos_valid = false;
     return PST_OK;
+}
+
+pst_status pst_resolve_history(pst_ctx* ctx) {
+    if (!ctx->hist_lag) return PST_OK;
+    ctx->hist_lag = false;
+    if (ctx->n == 0) return PST_OK;
+    return ctx->f64 ? launch_remap<double>(ctx) : launch_remap<float>(ctx);
 }
 
 pst_status pst_nnps_build(pst_ctx* ctx) {

@@ -70,6 +70,7 @@ struct pst_ctx {
     bool ordered = false;            // device order != id order (a sort has happened)
     bool nbrs_valid = false;
     bool eos_valid = false;
+    bool hist_lag = false;           // contact-history rows still sit at their PRE-sort index (vals_out maps new -> old)
     uint64_t launches = 0;
     cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)
     bool stats_pending = false;
@@ -117,6 +118,7 @@ int pst_option(pst_ctx* ctx, const char* name, int dflt = 0);
 // stage implementations (one per .cu)
 pst_status pst_nnps_build(pst_ctx* ctx);                                 // nnps.cu
 pst_status pst_nnps_alloc(pst_ctx* ctx);
+pst_status pst_resolve_history(pst_ctx* ctx);   // run the deferred k_remap_history, if any
 pst_status pst_nnps_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size_t cap, size_t* n_pairs);
 pst_status pst_reorder_upload(pst_ctx* ctx, PstArray* a, int row, size_t n);   // stage -> array (by id)
 pst_status pst_reorder_download(pst_ctx* ctx, PstArray* a, int row, size_t n); // array -> stage (by id)
