@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
 // at a time with their 16 loads in flight together and only records the hits, (3) the heavy contact body then
 // runs on the recorded hits.  The kernel is a latency-bound gather, so the win is memory-level parallelism.
 template <class R>
-__global__ void __launch_bounds__(kThreads) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
+__global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
     const R xi = A.x[s], yi = A.y[s], zi = A.z[s];

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== pytest dem"; timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -k "dem or checkpoint or golden" > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest.log
+echo skip
 summ='
 import sys, json
 for l in sys.stdin:
