@@ -59,6 +59,155 @@ __global__ void __launch_bounds__(kThreads) k_bounds(int n, uint32_t ncells, con
     for (long long k = prev + 1; k <= cur; ++k) cell_start[k] = s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hand-written cell sort (default; option sort_impl = 1): a counting sort over the cell keys that also PRODUCES the
+// cell table, so it replaces both the radix sort and k_bounds.
+//   k_keys_count   key per particle + provisional rank r = atomicAdd(count[key], 1)
+//   k_scan_*       exclusive scan of the counts, in place -> cell_start (prefix semantics), 3 small kernels
+//   k_place        slot[cell_start[key] + r] = previous index
+//   k_cell_order   per cell: sort its <= 32 slots ascending (cells with more go through k_cell_order_big)
+// The atomics make r nondeterministic; sorting each cell's slots by previous index restores exactly the order a
+// STABLE sort gives, so results are run-to-run reproducible and bit-identical to the CUB path (tested).
+// ---------------------------------------------------------------------------------------------
+template <class R, int DIM, bool MORTON>
+__global__ void __launch_bounds__(kThreads) k_keys_count(GridDev<R> g, int n, const R* __restrict__ x, const R* __restrict__ y,
+                                                         const R* __restrict__ z, uint32_t* __restrict__ keys, uint32_t* __restrict__ prov,
+                                                         int32_t* __restrict__ count, uint32_t ncells, int mig_l, int mig_r) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int cxu = (int)floor((x[s] - g.lo[0]) * g.inv_cell);
+    const int cx = min(max(cxu, g.cx_lo), g.cx_hi);
+    const int cy = cell_coord<R>(y[s], g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    uint32_t key = cell_key<DIM, MORTON>(g, cx, cy, cz);
+    if (mig_l && cxu < g.cx_lo) key = ncells;
+    else if (mig_r && cxu > g.cx_hi) key = ncells + 1u;
+    keys[s] = key;
+    prov[s] = (uint32_t)atomicAdd(&count[key], 1);
+}
+
+constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+// block-level exclusive scan of one tile, in place; tile total -> sums[blockIdx.x]; also counts non-empty cells
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(int m, int32_t* __restrict__ a, int32_t* __restrict__ sums,
+                                                             unsigned long long* __restrict__ counters) {
+    __shared__ int warp_tot[kScanThreads / 32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems], t = 0, occ = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = base + k < m ? a[base + k] : 0;
+        occ += v[k] != 0;
+        const int x = v[k]; v[k] = t; t += x;          // exclusive within the thread
+    }
+    int incl = t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    const int toff = woff + incl - t;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < m) a[base + k] = v[k] + toff;
+    if (threadIdx.x == kScanThreads - 1) sums[blockIdx.x] = woff + incl;
+    // occupied cells, for the tile-depth heuristic of the pair kernels
+    for (int d = 16; d > 0; d >>= 1) occ += __shfl_down_sync(0xffffffffu, occ, d);
+    if (lane == 0 && occ) atomicAdd(&counters[2], (unsigned long long)occ);
+}
+
+// single block: exclusive scan of the tile sums
+__global__ void __launch_bounds__(1024) k_scan_sums(int nb, int32_t* __restrict__ sums) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const int x = i < nb ? sums[i] : 0;
+        int incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+        const int carry = carry_s;
+        if (i < nb) sums[i] = carry + woff + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(int m, int32_t* __restrict__ a, const int32_t* __restrict__ sums) {
+    const int off = sums[blockIdx.x];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < m) a[base + k] += off;
+}
+
+__global__ void __launch_bounds__(kThreads) k_place(int n, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ prov,
+                                                    const int32_t* __restrict__ cell_start, uint32_t* __restrict__ slot) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) slot[cell_start[keys[s]] + prov[s]] = (uint32_t)s;
+}
+
+constexpr int kSmallCell = 32;
+// one thread per cell: insertion sort of its slots (nearly sorted already: the atomics arrive roughly in index order)
+__global__ void __launch_bounds__(kThreads) k_cell_order(uint32_t nkeys, const int32_t* __restrict__ cell_start, uint32_t* __restrict__ slot,
+                                                         uint32_t* __restrict__ big_list, unsigned long long* __restrict__ counters) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nkeys) return;
+    const int b = cell_start[c], e = cell_start[c + 1], cnt = e - b;
+    if (cnt <= 1) return;
+    if (cnt > kSmallCell) {
+        const unsigned long long k = atomicAdd(&counters[4], 1ull);
+        big_list[k] = c;                       // capacity nkeys: cannot overflow
+        return;
+    }
+    uint32_t v[kSmallCell];
+    for (int i = 0; i < cnt; ++i) v[i] = slot[b + i];
+    for (int i = 1; i < cnt; ++i) {
+        const uint32_t x = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+        v[j + 1] = x;
+    }
+    for (int i = 0; i < cnt; ++i) slot[b + i] = v[i];
+}
+
+// crowded cells (e.g. out-of-box particles clamped into an edge cell): one block per cell, rank by counting.
+// Values are distinct, so rank = #smaller is a permutation.  `tmp` is scratch of the same size as `slot`.
+__global__ void __launch_bounds__(256) k_cell_order_big(const int32_t* __restrict__ cell_start, uint32_t* __restrict__ slot,
+                                                        uint32_t* __restrict__ tmp, const uint32_t* __restrict__ big_list,
+                                                        const unsigned long long* __restrict__ counters) {
+    const unsigned long long nbig = counters[4];
+    for (unsigned long long q = blockIdx.x; q < nbig; q += gridDim.x) {
+        const uint32_t c = big_list[q];
+        const int b = cell_start[c], e = cell_start[c + 1];
+        for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+            const uint32_t x = slot[i];
+            int r = 0;
+            for (int j = b; j < e; ++j) r += slot[j] < x;
+            tmp[b + r] = x;
+        }
+        __syncthreads();
+        for (int i = b + threadIdx.x; i < e; i += blockDim.x) slot[i] = tmp[i];
+        __syncthreads();
+    }
+}
+
 constexpr int kMaxPermute = 40;
 struct PermuteList {
     const void* src[kMaxPermute];
@@ -153,6 +302,15 @@ pst_status launch_keys(pst_ctx* ctx, int mig_l, int mig_r) {
 }
 
 template <class R, int DIM, bool MORTON>
+pst_status launch_keys_count(pst_ctx* ctx, int mig_l, int mig_r) {
+    const int n = (int)ctx->n;
+    PST_LAUNCH(ctx, (k_keys_count<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n,
+               pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, ctx->keys_in, ctx->vals_in,
+               ctx->cell_start, ctx->grid.ncells, mig_l, mig_r);
+    return PST_OK;
+}
+
+template <class R, int DIM, bool MORTON>
 pst_status launch_dump(pst_ctx* ctx, int mode, const void* sz, uint32_t* oi, uint32_t* oj, size_t cap) {
     const int n = (int)ctx->n;
     PST_LAUNCH(ctx, (k_dump_pairs<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n, mode,
@@ -198,6 +356,7 @@ pst_status pst_nnps_alloc(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 8 * sizeof(int32_t), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stats, cudaEventDisableTiming));
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, (((size_t)ctx->grid.ncells + 4) / kScanTile + 2) * 4));
     ctx->sort_tmp_bytes = 0;
     PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, ctx->keys_in, ctx->keys_out, ctx->vals_in,
                                                   ctx->vals_out, (int)cap, 0, 32, ctx->stream));
@@ -221,21 +380,38 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     int key_bits = ctx->grid.key_bits;
     while (mig && (1ull << key_bits) < (unsigned long long)nkeys) ++key_bits;
     ctx->n_ghost_l = ctx->n_ghost_r = 0;
-    if (n > 0) {
-        PST_TRY(PST_DISPATCH(ctx, launch_keys, ctx, mig_l, mig_r));
-        size_t tmp = ctx->sort_tmp_bytes;
-        PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tmp, ctx->keys_in, ctx->keys_out, ctx->vals_in, ctx->vals_out,
-                                                      n, 0, key_bits, ctx->stream));
-        ctx->launches += (key_bits + 7) / 8 + 2;  // CUB onesweep: histogram + scan + one pass per 8 bits
-    }
     // occupied-cell count of the PREVIOUS build (read back asynchronously; the very first build waits once)
     if (ctx->stats_pending) {
         PST_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
         ctx->stats_pending = false;
         if (ctx->h_counters[2] > 0) ctx->params["_ppc"] = (double)ctx->h_counters[3] / (double)ctx->h_counters[2];
     }
-    PST_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(unsigned long long), ctx->stream));
-    PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, nkeys, ctx->keys_out, ctx->cell_start, ctx->d_counters);
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    if (pst_option(ctx, "sort_impl", 1) == 1) {
+        // ---- hand-written counting sort by cell key; the scanned counts ARE the cell table
+        const int m = (int)nkeys + 1;                       // entries [0, nkeys]: the last one becomes n
+        PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)nkeys + 2) * 4, ctx->stream));
+        if (n > 0) PST_TRY(PST_DISPATCH(ctx, launch_keys_count, ctx, mig_l, mig_r));
+        const int nb = (m + kScanTile - 1) / kScanTile;
+        PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums, ctx->d_counters);
+        PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
+        PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums);
+        if (n > 0) {
+            PST_LAUNCH(ctx, k_place, blocks_for(n), kThreads, 0, n, ctx->keys_in, ctx->vals_in, ctx->cell_start, ctx->vals_out);
+            PST_LAUNCH(ctx, k_cell_order, blocks_for(nkeys), kThreads, 0, nkeys, ctx->cell_start, ctx->vals_out, ctx->keys_out, ctx->d_counters);
+            PST_LAUNCH(ctx, k_cell_order_big, 296, 256, 0, ctx->cell_start, ctx->vals_out, ctx->vals_in, ctx->big_list(), ctx->d_counters);
+        }
+    } else {
+        // ---- library path (A/B): CUB onesweep radix sort on the key bits in use + k_bounds
+        if (n > 0) {
+            PST_TRY(PST_DISPATCH(ctx, launch_keys, ctx, mig_l, mig_r));
+            size_t tmp = ctx->sort_tmp_bytes;
+            PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tmp, ctx->keys_in, ctx->keys_out, ctx->vals_in, ctx->vals_out,
+                                                          n, 0, key_bits, ctx->stream));
+            ctx->launches += (key_bits + 7) / 8 + 2;  // CUB onesweep: histogram + scan + one pass per 8 bits
+        }
+        PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, nkeys, ctx->keys_out, ctx->cell_start, ctx->d_counters);
+    }
     PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaEventRecord(ctx->ev_stats, ctx->stream));
     ctx->h_counters[3] = (unsigned long long)n;

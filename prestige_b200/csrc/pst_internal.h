@@ -61,6 +61,8 @@ struct pst_ctx {
     uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
     int32_t* cell_start = nullptr;   // ncells + 1, signed: left ghosts live at negative indices
     void* sort_tmp = nullptr;
+    int32_t* scan_sums = nullptr;    // tile sums of the count scan (counting sort)
+    uint32_t* big_list() const { return keys_out; }   // crowded-cell list reuses keys_out (unused by the counting sort)
     size_t sort_tmp_bytes = 0;
     char* stage = nullptr;           // capacity * 8 bytes
     int32_t* d_flags = nullptr;      // [0] contact overflow, [1] pair counter lo, ... (8 ints)

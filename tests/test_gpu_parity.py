@@ -500,3 +500,38 @@ def test_golden_vectors_on_gpu():
         for k in ("fx", "fy", "fz", "tx", "ty", "tz"):
             assert_close(ctx.download(k), z[k], f"golden dem {k}")
         assert np.array_equal(ctx.download("hist_n"), z["hist_n"])
+
+
+# ------------------------------------------------------------------------------------------------
+# the hand-written counting sort must order particles exactly like the stable library radix sort
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["wcsph3d", "wcsph2d", "dem", "outside"])
+def test_counting_sort_equals_stable_radix_sort(which):
+    if which == "wcsph3d":
+        b = synth.wcsph_block_3d(31, 17, 23).shuffled()
+    elif which == "wcsph2d":
+        b = synth.wcsph_dambreak_2d(dx=0.02).shuffled()
+    elif which == "dem":
+        b = synth.dem_column_3d(16).shuffled()
+    else:                                   # most particles outside the box: thousands clamped into edge cells (crowded-cell path)
+        b = synth.wcsph_block_3d(24, 24, 24).shuffled()
+    kw = {}
+    if which == "outside":
+        kw = dict(lo=(0.05, 0.05, 0.05), hi=(0.08, 0.08, 0.08))
+    order, cells = {}, {}
+    for impl in (0, 1):
+        ctx = pb.context_for_block(b, **kw)
+        ctx.load_block(b)
+        ctx.set_option("sort_impl", impl)
+        for rep in range(3):
+            ctx.build_neighbours()
+        order[impl] = ctx.download("id")            # stable id held by each device slot
+        if b.physics == "wcsph":
+            ctx.apply(["tait_eos", "continuity", "momentum"])
+            cells[impl] = ctx.download("au")
+        else:
+            ctx.apply(["dem_contact"])
+            cells[impl] = ctx.download("fx")
+        ctx.close()
+    assert np.array_equal(order[0], order[1]), "device order differs from the stable sort"
+    assert np.array_equal(cells[0], cells[1]), "results must be bit-identical"
