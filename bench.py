@@ -74,6 +74,8 @@ def make_block(workload: str, rank: int = 0, world: int = 1):
         b.arrays = {k: np.ascontiguousarray(v[keep]) for k, v in b.arrays.items()}
         b.meta["ids"] = b.meta["ids"][keep]
         return b, (lo_x, hi_x)
+    if workload == "wcsph3d_80m":          # configs[3] on ONE GPU (strong-scaling reference point): 800 x 400 x 250
+        return synth.wcsph_block_3d(800, 400, 250, name="wcsph3d_80m"), None
     if workload == "dem3d_1m":
         return synth.dem_column_3d(100), None
     if workload == "dem3d_8m":
