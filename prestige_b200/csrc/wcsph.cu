@@ -195,7 +195,7 @@ struct TileDims {
     static constexpr int RY = DIM == 3 ? BB + 2 : 1;               // runs along y
 };
 
-constexpr int kListsJcap = 2048;   // float4 slots staged per tile (32 KB)
+constexpr int kListsJcap = 1536;   // float4 slots staged per tile (24 KB): every KB not requested stays L1 for the phase-2 gathers (2048 -> 1536: -3 %)
 
 template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
 __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
@@ -705,6 +705,7 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
     }
     G = std::min(std::max(G, 1), std::max(1, nf));
     G = std::min(G, (256 - 2 * D::NR - 2 * D::NI - 3) / D::NR - 3);   // boundary tables stay within 1 KB
+    while (user_G <= 0 && G > 1 && 1.08 * D::NR * (G + 2) * ppc > jc_max) --G;   // the staged runs must fit (else: slow exact fallback)
     T.G = G;
     T.tiles[0] = (g.n[0] + TA - 1) / TA;
     T.tiles[1] = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
