@@ -5,9 +5,10 @@ One "step" = cell keys -> radix sort -> cell table -> permute state (-> history 
 fused continuity+momentum pair kernel (or the DEM contact kernel) over one block of synthetic
 particles.  Integrator excluded.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wcsph3d_10m|dem3d_1m|wcsph2d_20k] [--real f64|f32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wcsph3d_10m|dem3d_1m|wcsph2d_20k|coupled3d_20m] [--real f64|f32]
     python bench.py --impl reference ...      # the CPU restatement (oracle/) on the host cores, same metric
     torchrun --nproc-per-node N bench.py --gpus N ...   # weak scaling: one ~10M-particle x-slab per rank
+                                                        # (coupled3d_20m: STRONG scaling, the 20M block cut into N slabs)
 
 Prints ONE JSON line (rank 0).
 """
@@ -43,6 +44,13 @@ def dem_bytes(real: str, zbar: float):
     return 250 + 64 * zbar, 87 + 2 * (16 * zbar + 4)
 
 
+def coupled_bytes(real: str, zbar_solid: float, f_solid: float):
+    """Coupled SPH-DEM: particle-weighted sum of the WCSPH and DEM columns; boundaries count as SPH."""
+    ds, df = dem_bytes(real, zbar_solid)
+    ws, wf = B_ALG[("wcsph", 3, real)], B_FORCE[("wcsph", 3, real)]
+    return (1 - f_solid) * ws + f_solid * ds, (1 - f_solid) * wf + f_solid * df
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -72,6 +80,22 @@ def make_block(workload: str, rank: int = 0, world: int = 1):
         b = synth.wcsph_block_3d(p1 - p0, 200, 250, dx=dx, ix0=p0, nx_total=nx_total, name="wcsph3d_10m_slab")
         keep = (b.arrays["x"] >= lo_x) & (b.arrays["x"] < hi_x)
         b.arrays = {k: np.ascontiguousarray(v[keep]) for k, v in b.arrays.items()}
+        b.meta["ids"] = b.meta["ids"][keep]
+        return b, (lo_x, hi_x)
+    if workload.startswith("coupled3d_"):   # configs[4]: rigid spheres in fluid; N > 1 cuts the SAME block into x-slabs (strong scaling)
+        from prestige_b200 import decomp
+        nx, ny, nz = {"20m": (250, 250, 320), "2m": (125, 125, 128), "300k": (64, 64, 72)}[workload.split("_")[1]]
+        if world == 1:
+            return synth.coupled_block_3d(nx, ny, nz), None
+        dx = 0.005
+        cell = 2.0 * 1.2 * dx * synth.CELL_MARGIN
+        first, k = decomp.split_layers(int(math.ceil(nx * dx / cell)), world)[rank]
+        lo_x, hi_x = first * cell, (first + k) * cell
+        p0 = max(0, int(math.floor(lo_x / dx)) - 1)
+        p1 = min(nx, int(math.ceil(hi_x / dx)) + 1)
+        b = synth.coupled_block_3d(p1 - p0, ny, nz, dx=dx, ix0=p0, nx_total=nx)
+        keep = decomp.owner_mask(b.arrays["x"], lo_x, hi_x, rank == 0, rank == world - 1)
+        b.arrays = {k_: np.ascontiguousarray(v[keep]) for k_, v in b.arrays.items()}
         b.meta["ids"] = b.meta["ids"][keep]
         return b, (lo_x, hi_x)
     if workload == "wcsph3d_80m":          # configs[3] on ONE GPU (strong-scaling reference point): 800 x 400 x 250
@@ -148,6 +172,8 @@ def cpu_sample_block(workload: str):
         return synth.wcsph_block_3d(100, 100, 100), "first 100x100x100 lattice planes (1.0 M particles) of the same generator"
     if workload.startswith("dem3d"):
         return synth.dem_column_3d(64), "64^3 spheres + floor (0.27 M particles) of the same generator"
+    if workload.startswith("coupled3d"):
+        return synth.coupled_block_3d(100, 100, 96), "100x100x96 lattice + floor (0.99 M particles, 10 % spheres) of the same generator"
     return synth.wcsph_dambreak_2d(dx=0.01), "the full 2D dam break (23 k particles)"
 
 
@@ -160,8 +186,10 @@ def cpu_step_time(block, reps: int):
         t0 = time.perf_counter()
         if block.physics == "wcsph":
             orc.wcsph(block.dim, block.params, block.arrays, grid=g, sorted_step=True)
-        else:
+        elif block.physics == "dem":
             _, hist, _ = orc.dem(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
+        else:
+            _, hist, _ = orc.coupled(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
         best = min(best, time.perf_counter() - t0)
     return best, orc.num_threads()
 
@@ -188,8 +216,10 @@ def run_reference(args, rank: int):
         nonlocal hist
         if block.physics == "wcsph":
             orc.wcsph(block.dim, block.params, block.arrays, grid=g, sorted_step=True)
-        else:
+        elif block.physics == "dem":
             _, hist, _ = orc.dem(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
+        else:
+            _, hist, _ = orc.coupled(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
@@ -199,7 +229,8 @@ def run_reference(args, rank: int):
     val = block.n * args.steps / dt
     real = args.real
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.workload.startswith("coupled3d") else "weak",
             "vs_baseline": None, "dtype": real, "data": "synthetic",
             "config": {"workload": args.workload, "sample": desc, "note": "CPU restatement (oracle/), not reference code: the reference has no runnable path (SURVEY.md 0.1)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": desc},
@@ -274,9 +305,10 @@ def main():
     lo, hi = list(block.lo), list(block.hi)
     if world > 1:
         if slab is None:
-            raise SystemExit("multi-GPU is implemented for the wcsph3d_10m slab workload")
+            raise SystemExit("multi-GPU is implemented for the wcsph3d_10m (weak) and coupled3d_* (strong) slab workloads")
         lo[0], hi[0] = slab
-        ghost_cap = int(2.0 * 200 * 250 * 3)
+        ny_p, nz_p = block.meta["lattice"][1], block.meta["lattice"][2]
+        ghost_cap = int(2.0 * ny_p * (nz_p + 3) * 3)
     cap = int(n * 1.02) + 1024
     ctx = pb.Context(dim=block.dim, lo=lo, hi=hi, cell_size=block.cell_size, capacity=cap, real=real, physics=block.physics,
                      key=args.key, max_contacts=block.max_contacts, device=local_rank, ghost_capacity=ghost_cap)
@@ -290,7 +322,8 @@ def main():
         ctx.comm_init(uid[0], rank, world)
     ctx.load_block(block)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    pair_eqs = ["continuity", "momentum"] if block.physics == "wcsph" else ["dem_contact"]
+    coupled = block.physics == "wcsph+dem"
+    pair_eqs = ["dem_contact"] if block.physics == "dem" else ["continuity", "momentum"]
 
     def step(ev=None):
         if ev: ev[0].record(stream)
@@ -298,11 +331,14 @@ def main():
         if world > 1:
             ctx.halo_exchange()
         if ev: ev[1].record(stream)
-        if block.physics == "wcsph":
+        if block.physics != "dem":
             ctx.apply(["tait_eos"])
         if ev: ev[2].record(stream)
         ctx.apply(pair_eqs)
         if ev: ev[3].record(stream)
+        if coupled:
+            ctx.apply(["dem_contact"])
+        if ev: ev[4].record(stream)
 
     def barrier():
         if world > 1:
@@ -316,7 +352,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     l0 = ctx.stat("launches")
     barrier()
     t0 = time.perf_counter()
@@ -326,21 +362,28 @@ def main():
     wall = time.perf_counter() - t0
     launches = ctx.stat("launches") - l0
     clocks = sampler.stop() if rank == 0 else None
-    t_dev = evs[0][0].elapsed_time(evs[-1][3]) * 1e-3         # device time of the whole timed region
+    t_dev = evs[0][0].elapsed_time(evs[-1][4]) * 1e-3         # device time of the whole timed region
     t_nnps = sum(e[0].elapsed_time(e[1]) for e in evs) * 1e-3 / args.steps
     t_eos = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / args.steps
     t_force = sum(e[2].elapsed_time(e[3]) for e in evs) * 1e-3 / args.steps
-    zbar = 0.0
+    t_dem = sum(e[3].elapsed_time(e[4]) for e in evs) * 1e-3 / args.steps
+    zbar, n_solid = 0.0, 0
     if block.physics == "dem":
         zbar = ctx.stat("contacts_total") / n
+    elif coupled:
+        n_solid = int((block.arrays["tag"] == 2).sum())
+        zbar = ctx.stat("contacts_total") / max(n_solid, 1)     # mean stored contacts per SPHERE
     n_total, t_max = n, t_dev
     if world > 1:
         tt = torch.tensor([t_dev, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_max = float(tt[0])
-        nn = torch.tensor([n], device="cuda", dtype=torch.int64)
+        nn = torch.tensor([n, n_solid, int(round(zbar * n_solid))], device="cuda", dtype=torch.int64)
         dist.all_reduce(nn)
-        n_total = int(nn[0])
+        n_total, n_solid_total = int(nn[0]), int(nn[1])
+        zbar_total = float(nn[2]) / max(n_solid_total, 1)
+    else:
+        n_solid_total, zbar_total = n_solid, zbar
     value = n_total * args.steps / t_max
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -349,7 +392,8 @@ def main():
         lib = _lib.load()
         pin = Pinned(lib)
         ins = [k for k in block.arrays if ctx.has_array(k) and k not in ("tag", "m", "h", "rad", "inertia")]
-        outs = (["au", "av", "aw", "arho"] if block.dim == 3 else ["au", "av", "arho"]) if block.physics == "wcsph" else ["fx", "fy", "fz", "tx", "ty", "tz"]
+        outs = (["au", "av", "aw", "arho"] if block.dim == 3 else ["au", "av", "arho"]) if block.physics != "dem" else []
+        outs += ["fx", "fy", "fz", "tx", "ty", "tz"] if block.physics != "wcsph" else []
         hin = {k: pin.array(n, block.arrays[k].dtype) for k in ins}
         for k in ins:
             hin[k][:] = block.arrays[k]
@@ -382,7 +426,7 @@ def main():
             te = float(tt[0])
         e2e = {"value": n_total * e2e_steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e2e_steps, "ms_per_step": te / e2e_steps * 1e3,
-               "path": "pst_upload_async(7 state arrays, pinned host) -> pst_build_neighbours -> pst_apply -> pst_download_async(rates, pinned host), pst_sync at the end"}
+               "path": f"pst_upload_async({len(ins)} state arrays, pinned host) -> pst_build_neighbours -> pst_apply -> pst_download_async({len(outs)} rate arrays, pinned host), pst_sync at the end"}
         pin.free()
 
     if rank == 0:
@@ -390,11 +434,15 @@ def main():
         key = (block.physics, block.dim, args.real)
         if block.physics == "dem":
             b_step, b_force = dem_bytes(args.real, zbar)
+        elif coupled:
+            # the SPH pass of a coupled step touches every particle's SPH columns; the contact pass is reported beside it
+            b_step, _ = coupled_bytes(args.real, zbar_total, n_solid_total / n_total)
+            b_force = B_FORCE[("wcsph", 3, args.real)]
         else:
             b_step, b_force = B_ALG[key], B_FORCE[key]
         n_local = n
         ach = b_force * n_local / t_force / 1e9
-        kern = ({1: "k_wcsph_cellwarp", 2: "k_wcsph_tiled"}.get(args.force_kernel, "k_wcsph_gather") if args.key == "linear" else "k_wcsph_gather") if block.physics == "wcsph" else "k_dem_forces"
+        kern = ({1: "k_wcsph_cellwarp", 2: "k_wcsph_tiled"}.get(args.force_kernel, "k_wcsph_gather") if args.key == "linear" else "k_wcsph_gather") if block.physics != "dem" else "k_dem_forces"
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -406,15 +454,18 @@ def main():
                     "step": {"alg_bytes_per_particle": b_step, "achieved": b_step * n_total / (t_max / args.steps) / 1e9 / world,
                              "frac": b_step * n_total / (t_max / args.steps) / 1e9 / world / peak},
                     "stage_ms": {"nnps(keys+sort+table+permute" + ("+halo)" if world > 1 else ")"): t_nnps * 1e3, "eos": t_eos * 1e3, "pair_kernel": t_force * 1e3}}
+        if coupled:
+            roofline["stage_ms"]["contact_kernel"] = t_dem * 1e3
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if coupled else "weak", "vs_baseline": None,
                 "dtype": args.real, "data": "synthetic",
                 "config": {"workload": args.workload, "particles": n_total, "particles_per_gpu": n_local, "dim": block.dim,
                            "physics": block.physics, "key": args.key, "force_kernel": kern,
-                           "decomposition": f"{world} x-slabs of {SLAB_CELLS} cell layers, NCCL send/recv halo" if world > 1 else "single GPU",
+                           "decomposition": (f"{world} x-slabs of the same block, NCCL send/recv halo" if coupled else f"{world} x-slabs of {SLAB_CELLS} cell layers, NCCL send/recv halo") if world > 1 else "single GPU",
                            "l2": f"no flush needed: state + outputs = {n_local * (b_step) / 1e6:.0f} MB touched per step >> 126 MB L2",
-                           "timed": "keys+sort+cell table+permute" + ("+history remap" if block.physics == "dem" else "") + ("+halo exchange" if world > 1 else "") + "+EOS+fused pair kernel; integrator excluded",
-                           "mean_contacts": zbar if block.physics == "dem" else None},
+                           "timed": "keys+sort+cell table+permute" + ("+history remap" if block.physics != "wcsph" else "") + ("+halo exchange" if world > 1 else "") + ("+contact kernel" if block.physics == "dem" else "+EOS+fused pair kernel" + ("+contact kernel" if coupled else "")) + "; integrator excluded",
+                           "mean_contacts": zbar_total if block.physics != "wcsph" else None,
+                           "spheres": n_solid_total if coupled else None},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps * 1e3,
                 "roofline": roofline}
         if not args.no_cpu_baseline:

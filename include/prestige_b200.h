@@ -67,6 +67,11 @@ typedef enum pst_key { PST_KEY_LINEAR = 0, PST_KEY_MORTON = 1 } pst_key;
 #define PST_PHYS_NONE 0u
 #define PST_PHYS_WCSPH 1u /* x y [z] u v [w] rho m h tag | p au av [aw] arho */
 #define PST_PHYS_DEM 2u   /* x y z u v w wx wy wz rad m inertia tag | fx fy fz tx ty tz | hist_* */
+/* PST_PHYS_WCSPH | PST_PHYS_DEM = coupled SPH-DEM, rigid spheres in fluid (3D): the union of both array sets in ONE
+ * cell grid (cell_size >= max(kfac h, 2 rad)).  tag 0 = fluid, 1 = static boundary (SPH dummy particle and, with
+ * rad > 0, DEM wall sphere), 2 = solid sphere.  SPH pairs need a fluid member and see a solid through its displaced
+ * fluid mass m rho0 / rho_solid; contacts are evaluated for solid i against non-fluid j; pst_step moves a solid by
+ * F_contact + m rho0/rho_solid (a_sph - g) + m g.  DESIGN.md "Coupled formulation". */
 
 /* array flags */
 #define PST_ARRAY_PERSISTENT 1u /* state: follows its particle through every re-sort */
@@ -98,7 +103,7 @@ PST_API const char* pst_last_error(const pst_ctx* ctx);
 PST_API void* pst_stream(pst_ctx* ctx);
 PST_API pst_status pst_sync(pst_ctx* ctx);
 
-/* named scalar parameters: rho0 c0 gamma alpha beta kfac gx gy gz | dem_model kn gn kt gt mu dt Estar Gstar erest */
+/* named scalar parameters: rho0 c0 gamma alpha beta kfac gx gy gz | dem_model kn gn kt gt mu dt Estar Gstar erest | rho_solid */
 PST_API pst_status pst_set_param(pst_ctx* ctx, const char* name, double value);
 PST_API pst_status pst_get_param(pst_ctx* ctx, const char* name, double* value);
 

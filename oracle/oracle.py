@@ -49,6 +49,7 @@ def lib():
             getattr(_LIB, f"orc_pairs_allpairs_{sfx}").restype = C.c_int64
             getattr(_LIB, f"orc_pairs_cells_{sfx}").restype = C.c_int64
             getattr(_LIB, f"orc_dem_forces_{sfx}").restype = C.c_int
+            getattr(_LIB, f"orc_coupled_forces_{sfx}").restype = C.c_int
     return _LIB
 
 
@@ -185,6 +186,62 @@ def dem(P: dict, K: int, a: dict, hist: dict | None = None, ids: np.ndarray | No
         _p(new["hist_n"]), _p(new["hist_id"]), _p(new["hist_x"]), _p(new["hist_y"]), _p(new["hist_z"]),
         _p(out["fx"]), _p(out["fy"]), _p(out["fz"]), _p(out["tx"]), _p(out["ty"]), _p(out["tz"]))
     return out, new, int(ov)
+
+
+def sph_mass(a: dict, P: dict) -> np.ndarray:
+    """SPH mass of every particle in a coupled block: m for fluid (tag 0) and boundary (tag 1), the displaced fluid
+    mass m * rho0 / rho_solid for solids (tag 2)."""
+    m = np.ascontiguousarray(a["m"])
+    ratio = m.dtype.type(P["rho0"]) / m.dtype.type(P["rho_solid"])
+    return np.where(a["tag"] == 2, m * ratio, m).astype(m.dtype)
+
+
+def coupled(P: dict, K: int, a: dict, hist: dict | None = None, ids: np.ndarray | None = None, grid: Grid | None = None):
+    """One coupled SPH-DEM force evaluation (3D).  Returns (rates + forces dict, new history dict, overflow flag)."""
+    x = np.ascontiguousarray(a["x"]); n = len(x); dt = x.dtype
+    hist = hist or empty_history(n, K, dt)
+    ids = np.arange(n, dtype=np.uint32) if ids is None else np.ascontiguousarray(ids, np.uint32)
+    new = empty_history(n, K, dt)
+    names_out = ("p", "au", "av", "aw", "arho", "fx", "fy", "fz", "tx", "ty", "tz")
+    out = {k: np.zeros(n, dt) for k in names_out}
+    ins = {k: np.ascontiguousarray(a[k], dt) for k in ("x", "y", "z", "u", "v", "w", "rho", "m", "h", "wx", "wy", "wz", "rad")}
+    ins["ms"] = sph_mass(a, P)
+    order = ("x", "y", "z", "u", "v", "w", "rho", "ms", "h", "wx", "wy", "wz", "rad", "m")
+    in_ptrs = (C.c_void_p * len(order))(*[ins[k].ctypes.data for k in order])
+    out_ptrs = (C.c_void_p * len(names_out))(*[out[k].ctypes.data for k in names_out])
+    wp, dp = wcsph_params(3, P), dem_params(P, K)
+    tag = np.ascontiguousarray(a["tag"], np.int32)
+    ov = getattr(lib(), f"orc_coupled_forces_{_sfx(x)}")(
+        C.byref(wp), C.byref(dp), C.byref(grid) if grid is not None else None, C.c_int64(n), in_ptrs, _p(tag), _p(ids),
+        _p(np.ascontiguousarray(hist["hist_n"])), _p(np.ascontiguousarray(hist["hist_id"])),
+        _p(np.ascontiguousarray(hist["hist_x"])), _p(np.ascontiguousarray(hist["hist_y"])),
+        _p(np.ascontiguousarray(hist["hist_z"])), out_ptrs,
+        _p(new["hist_n"]), _p(new["hist_id"]), _p(new["hist_x"]), _p(new["hist_y"]), _p(new["hist_z"]))
+    return out, new, int(ov)
+
+
+def coupled_integrate(a: dict, r: dict, P: dict, dt: float) -> dict:
+    """The documented semi-implicit Euler stage of a coupled context, on the host (numpy, same operation order
+    as k_coupled_integrate): every particle rho += arho dt; fluid v += a dt, x += v dt; solids
+    v += (F/m + (rho0/rho_solid)(a - g) + g) dt, x += v dt, omega += T/I dt; boundaries keep x, v."""
+    T = a["x"].dtype.type
+    dt = T(dt)
+    new = {k: np.array(v, copy=True) for k, v in a.items()}
+    tag = a["tag"]
+    fl, so = tag == 0, tag == 2
+    g = [T(P.get("gx", 0.0)), T(P.get("gy", 0.0)), T(P.get("gz", 0.0))]
+    ratio = T(P["rho0"]) / T(P["rho_solid"])
+    new["rho"] = a["rho"] + r["arho"] * dt
+    im = T(1) / a["m"]
+    ii = T(1) / np.where(so, a["inertia"], T(1))
+    for ax, (pos, vel, acc, frc, gk) in enumerate((("x", "u", "au", "fx", g[0]), ("y", "v", "av", "fy", g[1]), ("z", "w", "aw", "fz", g[2]))):
+        a_s = (r[frc] * im + ratio * (r[acc] - gk)) + gk
+        vn = np.where(fl, a[vel] + r[acc] * dt, np.where(so, a[vel] + a_s * dt, a[vel]))
+        new[vel] = vn
+        new[pos] = np.where(fl | so, a[pos] + vn * dt, a[pos])
+    for om, tq in (("wx", "tx"), ("wy", "ty"), ("wz", "tz")):
+        new[om] = np.where(so, a[om] + r[tq] * ii * dt, a[om])
+    return new
 
 
 def history_as_dict(hist: dict, ids: np.ndarray | None = None) -> dict:

@@ -89,6 +89,7 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
     ctx->cfg = *cfg;
     ctx->f64 = cfg->real == PST_F64;
     ctx->dim = cfg->dim;
+    ctx->coupled = (cfg->physics & PST_PHYS_WCSPH) && (cfg->physics & PST_PHYS_DEM);
     ctx->capacity = cfg->capacity;
     ctx->ghost_cap = cfg->ghost_capacity;
     auto bail = [&](pst_status s) { g_create_err = ctx->err; pst_destroy(ctx); return s; };
@@ -133,7 +134,7 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
     // default parameters
     ctx->params = {{"rho0", 1000.0}, {"c0", 10.0}, {"gamma", 7.0}, {"alpha", 0.1}, {"beta", 0.0}, {"kfac", 2.0},
                    {"gx", 0.0}, {"gy", 0.0}, {"gz", 0.0}, {"dem_model", 0.0}, {"kn", 1e5}, {"gn", 0.0}, {"kt", 2e4},
-                   {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}};
+                   {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}, {"rho_solid", 2500.0}};
     pst_status s = PST_OK;
     auto mk = [&](const char* name, int dt, uint32_t fl, int rows = 1) { if (s == PST_OK) s = array_create(ctx, name, dt, fl, rows); };
     const uint32_t P = PST_ARRAY_PERSISTENT, O = PST_ARRAY_OUTPUT;
@@ -148,6 +149,7 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
         mk("p", PST_REAL, O); mk("por2", PST_REAL, O);
         mk("au", PST_REAL, O); mk("av", PST_REAL, O); if (cfg->dim == 3) mk("aw", PST_REAL, O);
         mk("arho", PST_REAL, O);
+        if (ctx->coupled) mk("msph", PST_REAL, O);   // signed SPH mass, written by the EOS pass
     }
     if (cfg->physics & PST_PHYS_DEM) {
         mk("wx", PST_REAL, P); mk("wy", PST_REAL, P); mk("wz", PST_REAL, P);
@@ -264,7 +266,7 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     PST_TRY(st);
     PST_CUDA(ctx, cudaEventRecord(ctx->ring_free[k], ctx->stream));
     if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
-    if (a->name == "rho") ctx->eos_valid = false;
+    if (a->name == "rho" || a->name == "m" || a->name == "tag") ctx->eos_valid = false;
     return PST_OK;
 }
 
@@ -388,7 +390,7 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
         }
     }
     if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
-    if (a->name == "rho") ctx->eos_valid = false;
+    if (a->name == "rho" || a->name == "m" || a->name == "tag") ctx->eos_valid = false;
     return PST_OK;
 }
 
@@ -447,7 +449,9 @@ pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
     if (eqs.count("tait_eos")) PST_TRY(pst_wcsph_eos(ctx));
     if (eqs.count("continuity") || eqs.count("momentum")) {
         if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pair equations");
-        if (eqs.count("momentum") && !ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "momentum reads p: apply tait_eos first (or in the same set)");
+        if ((eqs.count("momentum") || ctx->coupled) && !ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "momentum reads p: apply tait_eos first (or in the same set)");
+        if (ctx->coupled && !(eqs.count("continuity") && eqs.count("momentum")))
+            return pst_fail(ctx, PST_EINVAL, "coupled contexts fuse continuity and momentum: apply both in one set");
         PST_TRY(pst_wcsph_forces(ctx, eqs.count("continuity") > 0, eqs.count("momentum") > 0));
     }
     if (eqs.count("dem_contact")) {
@@ -467,8 +471,9 @@ pst_status pst_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size
 pst_status pst_integrate(pst_ctx* ctx, double dt) {
     if (!ctx) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    if (ctx->cfg.physics & PST_PHYS_WCSPH) PST_TRY(pst_wcsph_integrate(ctx, dt));
-    if (ctx->cfg.physics & PST_PHYS_DEM) PST_TRY(pst_dem_integrate(ctx, dt));
+    if (ctx->coupled) PST_TRY(pst_coupled_integrate(ctx, dt));
+    else if (ctx->cfg.physics & PST_PHYS_WCSPH) PST_TRY(pst_wcsph_integrate(ctx, dt));
+    else if (ctx->cfg.physics & PST_PHYS_DEM) PST_TRY(pst_dem_integrate(ctx, dt));
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;
     return PST_OK;

@@ -26,6 +26,7 @@ template <class R>
 struct DemArgs {
     const R *x, *y, *z, *u, *v, *w, *wx, *wy, *wz, *rad, *m;
     const uint32_t* id;
+    const int32_t* tag;      // coupled SPH-DEM contexts only (else nullptr): i must be a solid (tag 2), j must not be fluid (tag 0)
     const int32_t* hn_in; const uint32_t* hid_in; const R *hx_in, *hy_in, *hz_in;
     const uint32_t* hperm;   // deferred history remap: old row of particle s is hperm[s] (nullptr: rows already in place)
     int32_t* hn_out; uint32_t* hid_out; R *hx_out, *hy_out, *hz_out;
@@ -121,6 +122,7 @@ template <class R, bool MORTON>
 __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
+    if (A.tag && A.tag[s] != 2) { dem_finish<R>(C, A, s, 0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0); return; }
     const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
     const R ui = A.u[s], vi = A.v[s], wi = A.w[s];
     const R ri = A.rad[s], mi = A.m[s];
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
             const R r2 = dist2<3, R>(dx, dy, dz);
             const R rs = add_rn(ri, A.rad[j]);
             if (!(r2 < mul_rn(rs, rs)) || !(r2 > (R)0) || j == s) continue;
+            if (A.tag && A.tag[j] == 0) continue;
             dem_contact<R>(C, A, s, j, xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
         }
     });
@@ -151,6 +154,7 @@ template <class R>
 __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
+    if (A.tag && A.tag[s] != 2) { dem_finish<R>(C, A, s, 0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0); return; }
     const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
     const R ri = A.rad[s];
     const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
@@ -173,16 +177,18 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
     for (int k = 0; k < 9; ++k) {
         for (int j0 = rb[k]; j0 < re[k]; j0 += 4) {
             R r2[4], rs[4];
+            int tg[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int j = min(j0 + t, re[k] - 1);
                 r2[t] = dist2<3, R>(xi - A.x[j], yi - A.y[j], zi - A.z[j]);
                 rs[t] = add_rn(ri, A.rad[j]);
+                tg[t] = A.tag ? A.tag[j] : 1;
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int j = j0 + t;
-                if (j < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != s) {
+                if (j < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != s && tg[t] != 0) {
                     if (nh < kHits) hits[nh] = j;
                     ++nh;
                 }
@@ -238,6 +244,7 @@ pst_status launch_dem(pst_ctx* ctx) {
     A.u = pst_ptr<R>(ctx, "u"); A.v = pst_ptr<R>(ctx, "v"); A.w = pst_ptr<R>(ctx, "w");
     A.wx = pst_ptr<R>(ctx, "wx"); A.wy = pst_ptr<R>(ctx, "wy"); A.wz = pst_ptr<R>(ctx, "wz");
     A.rad = pst_ptr<R>(ctx, "rad"); A.m = pst_ptr<R>(ctx, "m"); A.id = pst_ptr<uint32_t>(ctx, "id");
+    A.tag = ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr;
     const int c = hn->cur, d = 1 - hn->cur;
     A.hn_in = pst_ptr<int32_t>(ctx, hn, 0, c); A.hid_in = pst_ptr<uint32_t>(ctx, hid, 0, c);
     A.hx_in = pst_ptr<R>(ctx, hx, 0, c); A.hy_in = pst_ptr<R>(ctx, hy, 0, c); A.hz_in = pst_ptr<R>(ctx, hz, 0, c);

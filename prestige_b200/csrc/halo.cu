@@ -98,6 +98,7 @@ std::vector<PstArray*> ghost_arrays(pst_ctx* ctx) {
     for (const char* nm : {"x", "y", "z", "u", "v", "w", "m"}) add(nm);
     if (ctx->cfg.physics & PST_PHYS_WCSPH) add("rho");
     if (ctx->cfg.physics & PST_PHYS_DEM) for (const char* nm : {"wx", "wy", "wz", "rad", "id"}) add(nm);
+    if (ctx->coupled) add("tag");   // the signed SPH mass (k_eos) and the contact mask need it on ghosts too
     return v;
 }
 

@@ -266,10 +266,12 @@ __global__ void __launch_bounds__(kThreads) k_scatter_by_id(int n, const uint32_
 }
 
 // Neighbour / contact set dump (parity hook).  mode 0: r2 < (kfac*s_i)^2, s = h.  mode 1: r2 < (s_i+s_j)^2, s = rad.
+// Coupled contexts pass `tag`: mode 0 keeps the pairs with a fluid member, mode 1 those with a solid i and a non-fluid j.
 template <class R, int DIM, bool MORTON>
 __global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, int mode, R kfac, const int32_t* __restrict__ cell_start,
                                                          const R* __restrict__ x, const R* __restrict__ y, const R* __restrict__ z,
                                                          const R* __restrict__ sz, const uint32_t* __restrict__ id,
+                                                         const int32_t* __restrict__ tag,
                                                          uint32_t* __restrict__ oi, uint32_t* __restrict__ oj,
                                                          unsigned long long cap, unsigned long long* __restrict__ counter) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,9 +281,12 @@ __global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, in
     const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
     const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
     const uint32_t idi = id[s];
+    const int ti = tag ? tag[s] : 0;
+    if (tag && mode == 1 && ti != 2) return;
     for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
         for (int j = b; j < e; ++j) {
             if (j == s) continue;
+            if (tag && (mode == 0 ? (ti != 0 && tag[j] != 0) : tag[j] == 0)) continue;
             const R r2 = dist2<DIM, R>(xi - x[j], yi - y[j], DIM == 3 ? zi - z[j] : (R)0);
             const R rc = mode == 0 ? mul_rn(kfac, si) : add_rn(si, sz[j]);
             if (r2 < mul_rn(rc, rc)) {
@@ -315,7 +320,8 @@ pst_status launch_dump(pst_ctx* ctx, int mode, const void* sz, uint32_t* oi, uin
     const int n = (int)ctx->n;
     PST_LAUNCH(ctx, (k_dump_pairs<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n, mode,
                (R)pst_param(ctx, "kfac", 2.0), ctx->cell_start, pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"),
-               DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, (const R*)sz, pst_ptr<uint32_t>(ctx, "id"), oi, oj,
+               DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, (const R*)sz, pst_ptr<uint32_t>(ctx, "id"),
+               ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr, oi, oj,
                (unsigned long long)cap, ctx->d_counters);
     return PST_OK;
 }

@@ -41,6 +41,7 @@ struct PstComm;  // halo.cu
 struct pst_ctx {
     pst_config cfg{};
     bool f64 = true;
+    bool coupled = false;    // physics = WCSPH | DEM: rigid spheres in fluid (tags 0 fluid, 1 boundary, 2 solid)
     int dim = 3;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pst_upload_async / pst_download_async
@@ -131,6 +132,7 @@ pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum);
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu
 pst_status pst_dem_integrate(pst_ctx* ctx, double dt);
+pst_status pst_coupled_integrate(pst_ctx* ctx, double dt);                // wcsph.cu
 pst_status pst_comm_destroy(pst_ctx* ctx);                                // halo.cu
 void pst_comm_neighbours(pst_ctx* ctx, int* has_left, int* has_right);
 pst_status pst_migrate(pst_ctx* ctx, int* arrivals);   // after a build pass with sentinel keys: ship leavers, append arrivals

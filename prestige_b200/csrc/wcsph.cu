@@ -43,11 +43,19 @@ WcsphConst<R> make_const(pst_ctx* ctx) {
 // EOS: p = B((rho/rho0)^gamma - 1) = B expm1(gamma log1p(rho/rho0 - 1)), and p/rho^2 which is what the momentum body consumes.
 // Runs over owned + ghost particles.
 // ---------------------------------------------------------------------------------------------
+// Coupled SPH-DEM contexts (DESIGN.md "Coupled formulation") also get `msph`, the SPH mass the pair kernels read in
+// place of m: +m for fluid, -m for boundaries, -m rho0/rho_solid (the displaced fluid mass) for solids.  The sign
+// carries "is fluid" into the pair loop without another gather: a pair is active iff one of its two particles is fluid.
 template <class R>
 __global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, const R* __restrict__ rho, R* __restrict__ p,
-                                             R* __restrict__ por2) {
+                                             R* __restrict__ por2, const int32_t* __restrict__ tag, const R* __restrict__ m,
+                                             R* __restrict__ msph, R solid_ratio) {
     const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= hi) return;
+    if (msph) {
+        const int t = tag[s];
+        msph[s] = t == 0 ? m[s] : (t == 2 ? -(m[s] * solid_ratio) : -m[s]);
+    }
     const R r = rho[s];
     // (rho/rho0)^gamma - 1 without cancellation near rho0 (same form as the oracle)
     const R e = (r - C.rho0) / C.rho0;
@@ -142,7 +150,8 @@ __device__ __forceinline__ void store_acc(const ForceArgs<R>& A, const WcsphCons
 // ---------------------------------------------------------------------------------------------
 // variant 0: per-particle gather
 // ---------------------------------------------------------------------------------------------
-template <class R, int DIM, bool MORTON, bool CONT, bool MOM>
+// COUPLED: A.m is the signed SPH mass (k_eos); the pair (i, j) counts iff i or j is fluid (mass > 0).
+template <class R, int DIM, bool MORTON, bool CONT, bool MOM, bool COUPLED = false>
 __device__ __forceinline__ void gather_one(const GridDev<R>& g, const WcsphConst<R>& C, const ForceArgs<R>& A, int s) {
     IState<R, DIM> I;
     load_i<R, DIM>(I, C, A.x[s], A.y[s], DIM == 3 ? A.z[s] : (R)0, A.u[s], A.v[s], DIM == 3 ? A.w[s] : (R)0, A.rho[s], A.por2[s], A.h[s]);
@@ -150,22 +159,26 @@ __device__ __forceinline__ void gather_one(const GridDev<R>& g, const WcsphConst
     const int cy = cell_coord<R>(I.y, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
     const int cz = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
     Acc<R> a{0, 0, 0, 0};
+    const bool fluid_i = !COUPLED || A.m[s] > (R)0;
     for_each_run<DIM, MORTON>(g, A.cell_start, cx, cy, cz, [&](int b, int e) {
         for (int j = b; j < e; ++j) {
             const R dx = I.x - A.x[j], dy = I.y - A.y[j], dz = DIM == 3 ? I.z - A.z[j] : (R)0;
             const R r2 = dist2<DIM, R>(dx, dy, dz);
-            if (r2 < I.rc2 && r2 > (R)0 && j != s)
-                pair_body<R, DIM, CONT, MOM>(C, I, dx, dy, dz, r2, A.u[j], A.v[j], DIM == 3 ? A.w[j] : (R)0, A.rho[j], A.m[j], A.por2[j], a);
+            if (r2 < I.rc2 && r2 > (R)0 && j != s) {
+                const R mj = A.m[j];
+                if (COUPLED && !(fluid_i || mj > (R)0)) continue;
+                pair_body<R, DIM, CONT, MOM>(C, I, dx, dy, dz, r2, A.u[j], A.v[j], DIM == 3 ? A.w[j] : (R)0, A.rho[j], COUPLED ? fabs(mj) : mj, A.por2[j], a);
+            }
         }
     });
     store_acc<R, DIM, CONT, MOM>(A, C, s, a);
 }
 
-template <class R, int DIM, bool MORTON, bool CONT, bool MOM>
+template <class R, int DIM, bool MORTON, bool CONT, bool MOM, bool COUPLED = false>
 __global__ void __launch_bounds__(kThreads) k_wcsph_gather(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
-    gather_one<R, DIM, MORTON, CONT, MOM>(g, C, A, s);
+    gather_one<R, DIM, MORTON, CONT, MOM, COUPLED>(g, C, A, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,7 +210,7 @@ struct TileDims {
 
 constexpr int kListsJcap = 1536;   // float4 slots staged per tile (24 KB): every KB not requested stays L1 for the phase-2 gathers (2048 -> 1536: -3 %)
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM>
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false>
 __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
     using D = TileDims<DIM, TA, TB>;
     constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
         for (int ii = tid; ii < ni; ii += NT) {
             int c = 0;
             while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
-            gather_one<R, DIM, false, CONT, MOM>(g, C, A, s_ibeg[c] + (ii - s_ipre[c]));
+            gather_one<R, DIM, false, CONT, MOM, COUPLED>(g, C, A, s_ibeg[c] + (ii - s_ipre[c]));
         }
         return;
     }
@@ -307,9 +320,11 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
         IState<R, DIM> I;
         Acc<R> a{0, 0, 0, 0}, a2{0, 0, 0, 0};
         float xf = 0, yf = 0, zf = 0, rc2f = 0;
+        bool fluid_i = true;
         if (active) {
             while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
             gi = s_ibeg[c] + (ii - s_ipre[c]);
+            if (COUPLED) fluid_i = A.m[gi] > (R)0;
             lx = c / BB; ly = c - lx * BB;
             load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
                            A.por2[gi], A.h[gi]);
@@ -380,7 +395,11 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
                 const bool in0 = r20 < I.rc2 && r20 > (R)0;            // the exact test (the set is defined here)
                 const bool in1 = v1 && r21 < I.rc2 && r21 > (R)0;
                 r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
-                const R m0 = in0 ? A.m[j0] : (R)0, m1 = in1 ? A.m[j1] : (R)0;
+                R m0 = in0 ? A.m[j0] : (R)0, m1 = in1 ? A.m[j1] : (R)0;
+                if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
+                    m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
+                    m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
+                }
                 pair_body<R, DIM, CONT, MOM>(C, I, dx0, dy0, dz0, r20, A.u[j0], A.v[j0], DIM == 3 ? A.w[j0] : (R)0, A.rho[j0], m0, A.por2[j0], a);
                 pair_body<R, DIM, CONT, MOM>(C, I, dx1, dy1, dz1, r21, A.u[j1], A.v[j1], DIM == 3 ? A.w[j1] : (R)0, A.rho[j1], m1, A.por2[j1], a2);
             }
@@ -655,7 +674,7 @@ ForceArgs<R> make_args(pst_ctx* ctx) {
     ForceArgs<R> A;
     A.x = pst_ptr<R>(ctx, "x"); A.y = pst_ptr<R>(ctx, "y"); A.z = pst_ptr<R>(ctx, "z");
     A.u = pst_ptr<R>(ctx, "u"); A.v = pst_ptr<R>(ctx, "v"); A.w = pst_ptr<R>(ctx, "w");
-    A.rho = pst_ptr<R>(ctx, "rho"); A.m = pst_ptr<R>(ctx, "m"); A.h = pst_ptr<R>(ctx, "h"); A.por2 = pst_ptr<R>(ctx, "por2");
+    A.rho = pst_ptr<R>(ctx, "rho"); A.m = pst_ptr<R>(ctx, ctx->coupled ? "msph" : "m"); A.h = pst_ptr<R>(ctx, "h"); A.por2 = pst_ptr<R>(ctx, "por2");
     A.au = pst_ptr<R>(ctx, "au"); A.av = pst_ptr<R>(ctx, "av"); A.aw = pst_ptr<R>(ctx, "aw"); A.arho = pst_ptr<R>(ctx, "arho");
     A.cell_start = ctx->cell_start;
     A.n = (int)ctx->n;
@@ -668,17 +687,21 @@ pst_status launch_gather(pst_ctx* ctx, bool cont, bool mom) {
     const WcsphConst<R> C = make_const<R>(ctx);
     const ForceArgs<R> A = make_args<R>(ctx);
     const unsigned grid = blocks_for(ctx->n, kThreads);
+    if (ctx->coupled) {
+        if (DIM == 3) PST_LAUNCH(ctx, (k_wcsph_gather<R, 3, MORTON, true, true, true>), grid, kThreads, 0, g, C, A);
+        return PST_OK;
+    }
     if (cont && mom) PST_LAUNCH(ctx, (k_wcsph_gather<R, DIM, MORTON, true, true>), grid, kThreads, 0, g, C, A);
     else if (cont) PST_LAUNCH(ctx, (k_wcsph_gather<R, DIM, MORTON, true, false>), grid, kThreads, 0, g, C, A);
     else PST_LAUNCH(ctx, (k_wcsph_gather<R, DIM, MORTON, false, true>), grid, kThreads, 0, g, C, A);
     return PST_OK;
 }
 
-template <class R, int DIM, int TA, int TB, int NT, int VARIANT, bool CONT, bool MOM>
+template <class R, int DIM, int TA, int TB, int NT, int VARIANT, bool CONT, bool MOM, bool COUPLED = false>
 pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
     void (*kern)(GridDev<R>, WcsphConst<R>, ForceArgs<R>, TileShape);
     if (VARIANT == 1) kern = k_wcsph_cellwarp<R, DIM, TA, TB, NT, CONT, MOM>;
-    else kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM>;
+    else kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM, COUPLED>;
     PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const unsigned grid = (unsigned)T.tiles[0] * T.tiles[1] * T.tiles[2];
     PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), make_args<R>(ctx), T);
@@ -716,6 +739,10 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
     const size_t smem = VARIANT == 1 ? (size_t)113 * 1024
                                      : ints + 4 * sizeof(double) + (size_t)kListsJcap * sizeof(float4) + (size_t)T.lcap * NT * sizeof(unsigned short);
     if (smem > 227 * 1024) return pst_fail(ctx, PST_EINVAL, "tile_lcap too large");
+    if (ctx->coupled) {
+        if (DIM == 3 && VARIANT == 2) return launch_tiled_k<R, 3, TA, TB, NT, 2, true, true, true>(ctx, T, smem);
+        return pst_fail(ctx, PST_EINVAL, "coupled contexts need dim = 3 and force_kernel 0 or 2");
+    }
     if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, true>(ctx, T, smem);
     if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, false>(ctx, T, smem);
     return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, false, true>(ctx, T, smem);
@@ -723,7 +750,8 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
 
 template <class R, int DIM, bool MORTON>
 pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
-    const int variant = pst_option(ctx, "force_kernel", 2);   // 2 = thread-per-particle lists (fastest measured), 1 = warp-per-cell, 0 = gather
+    int variant = pst_option(ctx, "force_kernel", 2);   // 2 = thread-per-particle lists (fastest measured), 1 = warp-per-cell, 0 = gather
+    if (ctx->coupled && variant == 1) variant = 2;      // the warp-per-cell kernel has no coupled form
     if (variant == 1 && !MORTON) return launch_tiled<R, DIM, 1, 2>(ctx, cont, mom);
     if (variant == 2 && !MORTON) return pst_option(ctx, "tile_ta", 2) == 3 ? launch_tiled<R, DIM, 2, 3>(ctx, cont, mom) : launch_tiled<R, DIM, 2, 2>(ctx, cont, mom);
     return launch_gather<R, DIM, MORTON>(ctx, cont, mom);
@@ -759,12 +787,67 @@ pst_status launch_integrate(pst_ctx* ctx, double dt) {
     return PST_OK;
 }
 
+// Coupled SPH-DEM stage (DESIGN.md "Coupled formulation"): every particle rho += arho dt; fluid (tag 0) v += a dt,
+// x += v dt; solids (tag 2) v += (F_contact/m + (rho0/rho_solid)(a - g) + g) dt, x += v dt, omega += T/I dt -- the SPH
+// sum `a` of a solid runs over its fluid neighbours only, so m_sph (a - g) is the hydrodynamic force on the sphere;
+// boundaries (tag 1) keep position and velocity.
+template <class R>
+struct CoupledIntArgs {
+    const int32_t* tag;
+    R *x, *y, *z, *u, *v, *w, *rho, *wx, *wy, *wz;
+    const R *m, *inertia, *au, *av, *aw, *arho, *fx, *fy, *fz, *tx, *ty, *tz;
+    R dt, g[3], ratio;
+    int n;
+};
+template <class R>
+__global__ void __launch_bounds__(256) k_coupled_integrate(CoupledIntArgs<R> A) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n) return;
+    const R dt = A.dt;
+    A.rho[s] += A.arho[s] * dt;
+    const int t = A.tag[s];
+    if (t == 1) return;
+    R ax = A.au[s], ay = A.av[s], az = A.aw[s];
+    if (t == 2) {
+        const R im = (R)1 / A.m[s], ii = (R)1 / A.inertia[s];
+        ax = (A.fx[s] * im + A.ratio * (ax - A.g[0])) + A.g[0];
+        ay = (A.fy[s] * im + A.ratio * (ay - A.g[1])) + A.g[1];
+        az = (A.fz[s] * im + A.ratio * (az - A.g[2])) + A.g[2];
+        A.wx[s] += A.tx[s] * ii * dt; A.wy[s] += A.ty[s] * ii * dt; A.wz[s] += A.tz[s] * ii * dt;
+    }
+    const R un = A.u[s] + ax * dt, vn = A.v[s] + ay * dt, wn = A.w[s] + az * dt;
+    A.u[s] = un; A.v[s] = vn; A.w[s] = wn;
+    A.x[s] += un * dt; A.y[s] += vn * dt; A.z[s] += wn * dt;
+}
+
+template <class R>
+pst_status launch_coupled_integrate(pst_ctx* ctx, double dt) {
+    CoupledIntArgs<R> A;
+    A.tag = pst_ptr<int32_t>(ctx, "tag");
+    A.x = pst_ptr<R>(ctx, "x"); A.y = pst_ptr<R>(ctx, "y"); A.z = pst_ptr<R>(ctx, "z");
+    A.u = pst_ptr<R>(ctx, "u"); A.v = pst_ptr<R>(ctx, "v"); A.w = pst_ptr<R>(ctx, "w"); A.rho = pst_ptr<R>(ctx, "rho");
+    A.wx = pst_ptr<R>(ctx, "wx"); A.wy = pst_ptr<R>(ctx, "wy"); A.wz = pst_ptr<R>(ctx, "wz");
+    A.m = pst_ptr<R>(ctx, "m"); A.inertia = pst_ptr<R>(ctx, "inertia");
+    A.au = pst_ptr<R>(ctx, "au"); A.av = pst_ptr<R>(ctx, "av"); A.aw = pst_ptr<R>(ctx, "aw"); A.arho = pst_ptr<R>(ctx, "arho");
+    A.fx = pst_ptr<R>(ctx, "fx"); A.fy = pst_ptr<R>(ctx, "fy"); A.fz = pst_ptr<R>(ctx, "fz");
+    A.tx = pst_ptr<R>(ctx, "tx"); A.ty = pst_ptr<R>(ctx, "ty"); A.tz = pst_ptr<R>(ctx, "tz");
+    A.dt = (R)dt;
+    A.g[0] = (R)pst_param(ctx, "gx"); A.g[1] = (R)pst_param(ctx, "gy"); A.g[2] = (R)pst_param(ctx, "gz");
+    A.ratio = (R)pst_param(ctx, "rho0") / (R)pst_param(ctx, "rho_solid", 1.0);
+    A.n = (int)ctx->n;
+    PST_LAUNCH(ctx, k_coupled_integrate<R>, blocks_for(A.n, 256), 256, 0, A);
+    return PST_OK;
+}
+
 template <class R>
 pst_status launch_eos(pst_ctx* ctx) {
     const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r;
     if (hi <= lo) return PST_OK;
+    const double rs = pst_param(ctx, "rho_solid", 0.0);
+    if (ctx->coupled && !(rs > 0)) return pst_fail(ctx, PST_EINVAL, "coupled context: parameter rho_solid must be > 0");
     PST_LAUNCH(ctx, k_eos<R>, blocks_for(hi - lo, 256), 256, 0, make_const<R>(ctx), lo, hi, pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "p"),
-               pst_ptr<R>(ctx, "por2"));
+               pst_ptr<R>(ctx, "por2"), ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr, pst_ptr<R>(ctx, "m"),
+               ctx->coupled ? pst_ptr<R>(ctx, "msph") : nullptr, ctx->coupled ? (R)pst_param(ctx, "rho0") / (R)rs : (R)0);
     return PST_OK;
 }
 
@@ -779,6 +862,11 @@ pst_status pst_wcsph_eos(pst_ctx* ctx) {
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum) {
     if (ctx->n == 0) return PST_OK;
     return PST_DISPATCH(ctx, launch_forces, ctx, continuity, momentum);
+}
+
+pst_status pst_coupled_integrate(pst_ctx* ctx, double dt) {
+    if (ctx->n == 0) return PST_OK;
+    return ctx->f64 ? launch_coupled_integrate<double>(ctx, dt) : launch_coupled_integrate<float>(ctx, dt);
 }
 
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt) {

@@ -19,7 +19,7 @@ _U64 = np.uint64
 _MASK = (1 << 64) - 1
 
 # field numbers (stable: they are part of the input definition)
-F_JX, F_JY, F_JZ, F_U, F_V, F_W, F_RHO, F_PERM = range(8)
+F_JX, F_JY, F_JZ, F_U, F_V, F_W, F_RHO, F_PERM, F_SOLID, F_WX, F_WY, F_WZ = range(12)
 
 
 def splitmix64(z: np.ndarray) -> np.ndarray:
@@ -51,7 +51,7 @@ class Block:
     """A synthetic particle block in id order plus everything a context needs."""
     name: str
     dim: int
-    physics: str                      # "wcsph" | "dem"
+    physics: str                      # "wcsph" | "dem" | "wcsph+dem" (coupled)
     arrays: dict                      # name -> np.ndarray (float64 / uint32 / int32)
     params: dict                      # pst_set_param names -> float
     lo: tuple
@@ -226,6 +226,66 @@ def dem_column_3d(n_side: int = 100, R: float = 1e-3, floor: bool = True, seed: 
     hi = (nx_total * sp, ny * sp, nz * sp)
     return Block("dem3d_column", 3, "dem", arr, P, lo, hi, cutoff * CELL_MARGIN, max_contacts=12,
                  meta={"R": R, "spacing": sp, "lattice": (nx_total, ny, nz), "ix0": ix0, "ids": gid.astype(np.uint32)})
+
+
+def coupled_block_3d(nx: int, ny: int, nz: int, dx: float = 0.005, solid_fraction: float = 0.3, floor: bool = True,
+                     ix0: int = 0, nx_total: int | None = None, seed: int = SEED, rho_solid: float = 2500.0) -> Block:
+    """C5 (BASELINE configs[4]): rigid spheres in fluid.  A jittered lattice block like C3 whose lower third holds
+    solid spheres (tag 2) on a hash-selected `solid_fraction` of the sites (10 % of all particles at 0.3), radius
+    0.505 dx so lattice-adjacent spheres overlap by ~1 % (contacts exist at step 0, as in C2), small random spin;
+    optional floor of 3 static boundary layers (tag 1) that are SPH dummy particles and DEM wall spheres at once.
+    `ix0`/`nx_total` select an x-slab of a wider block (ids and random fields are those of the global block)."""
+    nx_total = nx if nx_total is None else nx_total
+    ids, i, j, k = _lattice_ids(ix0, nx, ny, nz)
+    rho0 = 1000.0
+    h = 1.2 * dx
+    R = 0.505 * dx
+    P = wcsph_params(3, h, nz * dx)
+    P.update(dem_params(R, rho_s=rho_solid))
+    P["rho_solid"] = rho_solid
+    solid = (k < nz // 3) & (uniform01(ids, F_SOLID, seed) < solid_fraction)
+    jit = np.where(solid, 0.005 * R, 0.05 * dx)
+    x = (i + 0.5) * dx + (2.0 * uniform01(ids, F_JX, seed) - 1.0) * jit
+    y = (j + 0.5) * dx + (2.0 * uniform01(ids, F_JY, seed) - 1.0) * jit
+    z = (k + 0.5) * dx + (2.0 * uniform01(ids, F_JZ, seed) - 1.0) * jit
+    vs = np.where(solid, 0.01, 0.1 * P["c0"] * 0.01)
+    u = (2.0 * uniform01(ids, F_U, seed) - 1.0) * vs
+    v = (2.0 * uniform01(ids, F_V, seed) - 1.0) * vs
+    w = (2.0 * uniform01(ids, F_W, seed) - 1.0) * vs
+    wx = np.where(solid, usym(ids, F_WX, 1.0, seed), 0.0)
+    wy = np.where(solid, usym(ids, F_WY, 1.0, seed), 0.0)
+    wz = np.where(solid, usym(ids, F_WZ, 1.0, seed), 0.0)
+    tag = np.where(solid, 2, 0).astype(np.int32)
+    gid = ids
+    nl = 3 if floor else 0
+    if floor:
+        l, fi, fj = np.meshgrid(np.arange(nl, dtype=np.int64), np.arange(ix0, ix0 + nx, dtype=np.int64), np.arange(ny, dtype=np.int64), indexing="ij")
+        l, fi, fj = l.ravel(), fi.ravel(), fj.ravel()
+        fid = nx_total * ny * nz + (l * nx_total + fi) * ny + fj
+        nfl = len(fid)
+        x = np.concatenate([x, (fi + 0.5) * dx]); y = np.concatenate([y, (fj + 0.5) * dx]); z = np.concatenate([z, -(l + 0.5) * dx])
+        zero = np.zeros(nfl)
+        u, v, w = (np.concatenate([q, zero]) for q in (u, v, w))
+        wx, wy, wz = (np.concatenate([q, zero]) for q in (wx, wy, wz))
+        tag = np.concatenate([tag, np.ones(nfl, np.int32)])
+        gid = np.concatenate([ids, fid])
+    n = len(x)
+    is_solid = tag == 2
+    m_s = rho_solid * 4.0 / 3.0 * math.pi * R ** 3
+    m = np.where(is_solid, m_s, rho0 * dx ** 3)
+    arr = {
+        "x": x, "y": y, "z": z, "u": u, "v": v, "w": w,
+        "rho": rho0 * (1.0 + usym(gid, F_RHO, 1e-3, seed)),
+        "m": m, "h": np.full(n, h), "tag": tag,
+        "wx": wx, "wy": wy, "wz": wz,
+        "rad": np.where(tag == 0, 0.0, R), "inertia": np.where(is_solid, 0.4 * m_s * R * R, 1.0),
+    }
+    cutoff = 2.0 * h
+    lo = (0.0, 0.0, -nl * dx)
+    hi = (nx_total * dx, ny * dx, nz * dx)
+    return Block("coupled3d", 3, "wcsph+dem", arr, P, lo, hi, cutoff * CELL_MARGIN, max_contacts=12,
+                 meta={"dx": dx, "h": h, "R": R, "lattice": (nx_total, ny, nz), "ix0": ix0, "ids": gid.astype(np.uint32),
+                       "n_solid": int(is_solid.sum()), "n_boundary": int((tag == 1).sum())})
 
 
 def grid_dims(block: Block):

@@ -27,4 +27,16 @@ np.savez_compressed(os.path.join(HERE, "dem3d_small.npz"), **f2, **h2)
 c = synth.wcsph_dambreak_2d(dx=0.05).shuffled()
 r = orc.wcsph(2, c.params, c.arrays)
 np.savez_compressed(os.path.join(HERE, "wcsph2d_small.npz"), **r)
-print("golden vectors written")
+print("wcsph / dem golden vectors written")
+
+# coupled SPH-DEM (tags 0 fluid, 1 boundary, 2 solid): second evaluation, so the contact history is exercised
+k = synth.coupled_block_3d(9, 8, 9).shuffled()
+r1, h1, _ = orc.coupled(k.params, k.max_contacts, k.arrays)
+r2, h2, _ = orc.coupled(k.params, k.max_contacts, k.arrays, hist=h1)
+tag = k.arrays["tag"]
+nb, _ = orc.pairs(3, k.arrays["x"], k.arrays["y"], k.arrays["z"], k.arrays["h"])
+nb = nb[(tag[nb[:, 0]] == 0) | (tag[nb[:, 1]] == 0)]
+ct, _ = orc.pairs(3, k.arrays["x"], k.arrays["y"], k.arrays["z"], k.arrays["rad"], mode=1)
+ct = ct[(tag[ct[:, 0]] == 2) & (tag[ct[:, 1]] != 0)]
+np.savez_compressed(os.path.join(HERE, "coupled3d_small.npz"), x=k.arrays["x"], tag=tag, neighbours=nb, contacts=ct, hist_n=h2["hist_n"], **r2)
+print("coupled golden vectors written")

@@ -19,7 +19,7 @@ from oracle import oracle as orc                # noqa: E402
 from util import rel_err                        # noqa: E402
 
 
-def _slab_context(whole, rank, world, lr, extra_cap=0):
+def _slab_context(whole, rank, world, lr, extra_cap=0, physics="wcsph", max_contacts=0):
     cell = whole.cell_size
     n_layers = int(np.ceil((whole.hi[0] - whole.lo[0]) / cell))
     first, k = decomp.split_layers(n_layers, world)[rank]
@@ -27,7 +27,8 @@ def _slab_context(whole, rank, world, lr, extra_cap=0):
     own = decomp.owner_mask(whole.arrays["x"], lo, hi, rank == 0, rank == world - 1)
     n = int(own.sum())
     ctx = pb.Context(dim=3, lo=(lo, whole.lo[1], whole.lo[2]), hi=(hi, whole.hi[1], whole.hi[2]), cell_size=cell, capacity=n + extra_cap + 16,
-                     physics="wcsph", device=lr, ghost_capacity=decomp.ghost_capacity(24, 20, cell, whole.meta["dx"]))
+                     physics=physics, max_contacts=max_contacts, device=lr,
+                     ghost_capacity=decomp.ghost_capacity(24, 24, cell, whole.meta["dx"]))
     uid = [pb.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(uid[0], rank, world)
@@ -91,12 +92,55 @@ def migration(out, rank, world, lr):
                    "all_ids_once": bool(np.array_equal(flat, np.arange(whole.n)))}, f)
 
 
+def coupled(out, rank, world, lr):
+    """Coupled SPH-DEM across slab faces: spheres and fluid drift along +x, so contacts (with their history rows),
+    the signed SPH mass and the tag mask all have to work on ghosts and survive migration.  One evaluation against
+    the oracle, then pst_step on `world` ranks against the same steps on one GPU, matched by global id."""
+    whole = synth.coupled_block_3d(48, 16, 18)
+    whole.params["gz"] = 0.0
+    mob = whole.arrays["tag"] != 1
+    whole.arrays["u"] = whole.arrays["u"] + np.where(mob, 3.0, 0.0)
+    fields = ("au", "av", "aw", "arho", "fx", "fy", "fz", "tx", "ty", "tz")
+    ref, _, _ = orc.coupled(whole.params, whole.max_contacts, whole.arrays, grid=orc.make_grid(3, whole.lo, whole.hi, whole.cell_size))
+    ctx, own = _slab_context(whole, rank, world, lr, extra_cap=whole.n // 2, physics="wcsph+dem", max_contacts=whole.max_contacts)
+    ctx.build_neighbours()
+    ctx.halo_exchange()
+    ctx.apply(["tait_eos", "continuity", "momentum", "dem_contact"])
+    gid = ctx.download("id").astype(np.int64)
+    err1 = {c: rel_err(ctx.download(c), ref[c][gid]) for c in fields}
+    n0 = ctx.n
+    dt, steps = 1e-5, 200                        # drift 3 m/s * 2 ms = half a cell
+    ctx.step(dt, steps)
+    ctx.sync()
+    cnt = ctx.refresh_count()
+    gid = ctx.download("id").astype(np.int64)
+    state = ("x", "y", "z", "u", "rho", "wx", "wz")
+    got = {c: ctx.download(c) for c in state}
+    hn = ctx.download("hist_n")
+    ctx.close()
+    with pb.context_for_block(whole, device=lr) as one:
+        one.load_block(whole)
+        one.build_neighbours()
+        one.apply(["tait_eos", "continuity", "momentum", "dem_contact"])   # same call sequence as the slab ranks
+        one.step(dt, steps)
+        ref2 = {c: one.download(c) for c in state}
+        hn_ref = one.download("hist_n")
+    err = {c: float(np.max(np.abs(got[c] - ref2[c][gid]) / max(np.abs(ref2[c]).max(), 1e-300))) if len(gid) else 0.0 for c in state}
+    allg = [None] * world
+    dist.all_gather_object(allg, gid.tolist())
+    flat = np.sort(np.concatenate([np.array(g, dtype=np.int64) for g in allg]))
+    with open(os.path.join(out, f"rank{rank}.json"), "w") as f:
+        json.dump({"rank": rank, "world": world, "n0": n0, "n1": int(cnt), "moved": int(n0 != cnt), "err1": err1, "err": err,
+                   "hist_equal": bool(np.array_equal(hn, hn_ref[gid])), "contacts": int(hn.sum()),
+                   "all_ids_once": bool(np.array_equal(flat, np.arange(whole.n)))}, f)
+
+
 def main():
     out, mode = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "halo")
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    (halo_parity if mode == "halo" else migration)(out, rank, world, lr)
+    {"halo": halo_parity, "migration": migration, "coupled": coupled}[mode](out, rank, world, lr)
     dist.barrier(device_ids=[lr])
     dist.destroy_process_group()
 

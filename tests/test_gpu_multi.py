@@ -62,3 +62,26 @@ def test_migration_matches_single_gpu(world, tmp_path):
         for k, e in d["err"].items():
             assert e <= 1e-9, f"rank {rank} {k}: {e:.3e}"
     assert moved >= 2, "the drift must have pushed particles across at least one slab face"
+
+
+@pytest.mark.parametrize("world", [2])
+def test_coupled_sph_dem_across_slabs(world, tmp_path):
+    """Coupled SPH-DEM (BASELINE configs[4]) on slabs: one evaluation against the oracle, then 200 steps with halo
+    exchange and migration against the single-GPU run; contacts and their history survive the rank change."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(tmp_path), "coupled"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    moved = contacts = 0
+    for rank in range(world):
+        d = json.load(open(tmp_path / f"rank{rank}.json"))
+        assert d["all_ids_once"], "a particle was lost or duplicated in migration"
+        assert d["hist_equal"], "contact counts differ from the single-GPU run"
+        moved += d["moved"]; contacts += d["contacts"]
+        for k, e in d["err1"].items():
+            assert e <= 1e-10, f"rank {rank} evaluation {k}: {e:.3e}"
+        for k, e in d["err"].items():
+            assert e <= 1e-9, f"rank {rank} {k}: {e:.3e}"
+    assert moved >= 2 and contacts > 0
