@@ -147,14 +147,57 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
     dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
 }
 
+// Coupled SPH-DEM contexts: fluid particles share the (SPH-sized) cells, so a sphere's 27-cell stencil holds ~370
+// candidates of which only the non-fluid ones can be contact partners, and only ~1 thread in 10 is a sphere.  Each
+// contact pass therefore first compacts the NON-FLUID particles of the sorted order (owned + ghosts):
+//   k_nf_flags  pos[e] = (tag != 0), e = index - lo; also zeroes the outputs of the owned particles that are not spheres
+//   scan        exclusive, in place (nnps.cu): pos[e] = number of non-fluid particles before e, pos[hi - lo] = their total
+//   k_nf_fill   idx[pos[e]] = index
+// Because the compaction keeps the sorted order, a cell range [b, e) of the cell table maps to the contiguous range
+// [pos[b], pos[e]) of idx: the contact kernel runs one thread per compacted entry (full warps of spheres) and scans
+// compacted runs (no fluid candidates at all).
+struct NfArgs {
+    const int32_t* pos;   // hi - lo + 1 entries
+    const int32_t* idx;
+    int lo, hi;           // extended index range [-n_ghost_l, n + n_ghost_r)
+};
+
+template <class R>
+__global__ void __launch_bounds__(256) k_nf_flags(int lo, int hi, int n, const int32_t* __restrict__ tag, int32_t* __restrict__ pos,
+                                                  R* __restrict__ fx, R* __restrict__ fy, R* __restrict__ fz, R* __restrict__ tx,
+                                                  R* __restrict__ ty, R* __restrict__ tz, int32_t* __restrict__ hn_out) {
+    const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > hi) return;
+    if (s == hi) { pos[s - lo] = 0; return; }
+    const int t = tag[s];
+    pos[s - lo] = t != 0;
+    if (s >= 0 && s < n && t != 2) {
+        fx[s] = fy[s] = fz[s] = tx[s] = ty[s] = tz[s] = (R)0;
+        hn_out[s] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nf_fill(int lo, int hi, const int32_t* __restrict__ tag, const int32_t* __restrict__ pos,
+                                                 int32_t* __restrict__ idx) {
+    const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < hi && tag[s] != 0) idx[pos[s - lo]] = s;
+}
+
 // linear keys: (1) all 18 run bounds are fetched at once, (2) the contact TEST runs over the candidates four
 // at a time with their 16 loads in flight together and only records the hits, (3) the heavy contact body then
 // runs on the recorded hits.  The kernel is a latency-bound gather, so the win is memory-level parallelism.
-template <class R>
-__global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n) return;
-    if (A.tag && A.tag[s] != 2) { dem_finish<R>(C, A, s, 0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0); return; }
+// NF (coupled contexts): threads and candidates come from the compacted non-fluid list (see above).
+template <class R, bool NF>
+__global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A, NfArgs F) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (NF) {
+        if (s >= F.pos[F.hi - F.lo]) return;
+        s = F.idx[s];
+        if (s < 0 || s >= A.n || A.tag[s] != 2) return;      // ghosts and boundaries are partners only
+    } else {
+        if (s >= A.n) return;
+        if (A.tag && A.tag[s] != 2) { dem_finish<R>(C, A, s, 0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0); return; }
+    }
     const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
     const R ri = A.rad[s];
     const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
@@ -169,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
         const uint32_t k0 = ok ? ((uint32_t)ax * g.n[1] + ay) * g.n[2] : 0u;
         rb[k] = A.cell_start[k0 + zl];
         re[k] = ok ? A.cell_start[k0 + zh + 1] : rb[k];
+        if (NF) { rb[k] = F.pos[rb[k] - F.lo]; re[k] = F.pos[re[k] - F.lo]; }
     }
     constexpr int kHits = 32;          // >= max_contacts (<= 32)
     int hits[kHits];
@@ -179,16 +223,20 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
             R r2[4], rs[4];
             int tg[4];
 #pragma unroll
+            int jj[4];
+#pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int j = min(j0 + t, re[k] - 1);
+                const int q = min(j0 + t, re[k] - 1);
+                const int j = NF ? F.idx[q] : q;
+                jj[t] = j;
                 r2[t] = dist2<3, R>(xi - A.x[j], yi - A.y[j], zi - A.z[j]);
                 rs[t] = add_rn(ri, A.rad[j]);
-                tg[t] = A.tag ? A.tag[j] : 1;
+                tg[t] = (!NF && A.tag) ? A.tag[j] : 1;
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int j = j0 + t;
-                if (j < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != s && tg[t] != 0) {
+                const int j = NF ? jj[t] : j0 + t;
+                if (j0 + t < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != s && tg[t] != 0) {
                     if (nh < kHits) hits[nh] = j;
                     ++nh;
                 }
@@ -257,10 +305,26 @@ pst_status launch_dem(pst_ctx* ctx) {
     A.flags = ctx->d_flags;
     A.stride = ctx->capacity + 2 * ctx->ghost_cap;
     A.n = (int)ctx->n;
-    if (MORTON || pst_option(ctx, "dem_kernel", 1) == 0)
+    const int variant = MORTON ? 0 : pst_option(ctx, "dem_kernel", ctx->coupled ? 2 : 1);
+    NfArgs F{nullptr, nullptr, 0, 0};
+    if (variant == 0) {
         PST_LAUNCH(ctx, (k_dem_forces_generic<R, MORTON>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
-    else
-        PST_LAUNCH(ctx, (k_dem_forces<R>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
+    } else if (variant == 2 && ctx->coupled) {
+        // compact the non-fluid particles (owned + ghosts), then one thread per compacted entry
+        const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r, m = hi - lo + 1;
+        if (!ctx->nf_pos) {
+            const size_t cap = ctx->capacity + 2 * ctx->ghost_cap + 2;
+            if (cudaMalloc((void**)&ctx->nf_pos, cap * 4) != cudaSuccess || cudaMalloc((void**)&ctx->nf_idx, cap * 4) != cudaSuccess)
+                return pst_fail(ctx, PST_ENOMEM, "non-fluid compaction buffers");
+        }
+        PST_LAUNCH(ctx, k_nf_flags<R>, blocks_for(m, 256), 256, 0, lo, hi, A.n, A.tag, ctx->nf_pos, A.fx, A.fy, A.fz, A.tx, A.ty, A.tz, A.hn_out);
+        PST_TRY(pst_scan_exclusive(ctx, ctx->nf_pos, m));
+        PST_LAUNCH(ctx, k_nf_fill, blocks_for(m, 256), 256, 0, lo, hi, A.tag, ctx->nf_pos, ctx->nf_idx);
+        F = NfArgs{ctx->nf_pos, ctx->nf_idx, lo, hi};
+        PST_LAUNCH(ctx, (k_dem_forces<R, true>), blocks_for(m, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
+    } else {
+        PST_LAUNCH(ctx, (k_dem_forces<R, false>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
+    }
     for (PstArray* a : {hn, hid, hx, hy, hz}) a->cur = d;
     ctx->hist_lag = false;   // the pass wrote every row at its new index
     return PST_OK;

@@ -148,7 +148,8 @@ extern "C" pst_status pst_comm_init(pst_ctx* ctx, const void* id_bytes, int rank
     PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)g.ncells + 4) * 4, ctx->stream));
     PST_CUDA(ctx, cudaFree(ctx->scan_sums));
     ctx->scan_sums = nullptr;
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, (((size_t)g.ncells + 4) / 4096 + 2) * 4));
+    ctx->scan_sums_cap = ((size_t)g.ncells + 4) / 4096 + 2;
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     PstComm* c = new PstComm();
     c->rank = rank; c->nranks = n_ranks;
     const size_t layer = (size_t)g.n[1] * g.n[2] + 1;

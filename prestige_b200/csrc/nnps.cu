@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(int m, int32_t* __r
     if (threadIdx.x == kScanThreads - 1) sums[blockIdx.x] = woff + incl;
     // occupied cells, for the tile-depth heuristic of the pair kernels
     for (int d = 16; d > 0; d >>= 1) occ += __shfl_down_sync(0xffffffffu, occ, d);
-    if (lane == 0 && occ) atomicAdd(&counters[2], (unsigned long long)occ);
+    if (counters && lane == 0 && occ) atomicAdd(&counters[2], (unsigned long long)occ);
 }
 
 // single block: exclusive scan of the tile sums
@@ -362,7 +362,8 @@ pst_status pst_nnps_alloc(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 8 * sizeof(int32_t), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stats, cudaEventDisableTiming));
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, (((size_t)ctx->grid.ncells + 4) / kScanTile + 2) * 4));
+    ctx->scan_sums_cap = ((size_t)ctx->grid.ncells + 4) / kScanTile + 2;
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     ctx->sort_tmp_bytes = 0;
     PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, ctx->keys_in, ctx->keys_out, ctx->vals_in,
                                                   ctx->vals_out, (int)cap, 0, 32, ctx->stream));
@@ -457,6 +458,22 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     ctx->ordered = true;
     ctx->nbrs_valid = true;
     ctx->eos_valid = false;
+    return PST_OK;
+}
+
+// exclusive scan of m ints, in place (the three scan kernels of the counting sort; scan_sums must hold m / kScanTile + 1 entries)
+pst_status pst_scan_exclusive(pst_ctx* ctx, int32_t* a, int m) {
+    const int nb = (m + kScanTile - 1) / kScanTile;
+    if ((size_t)nb + 1 > ctx->scan_sums_cap) {
+        PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PST_CUDA(ctx, cudaFree(ctx->scan_sums));
+        ctx->scan_sums = nullptr;
+        ctx->scan_sums_cap = (size_t)nb + 2;
+        PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
+    }
+    PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, a, ctx->scan_sums, (unsigned long long*)nullptr);
+    PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
+    PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, a, ctx->scan_sums);
     return PST_OK;
 }
 

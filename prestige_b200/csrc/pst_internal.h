@@ -63,6 +63,8 @@ struct pst_ctx {
     int32_t* cell_start = nullptr;   // ncells + 1, signed: left ghosts live at negative indices
     void* sort_tmp = nullptr;
     int32_t* scan_sums = nullptr;    // tile sums of the count scan (counting sort)
+    size_t scan_sums_cap = 0;        // entries
+    int32_t *nf_pos = nullptr, *nf_idx = nullptr;   // coupled contexts: compacted non-fluid particles of the sorted order (dem.cu)
     uint32_t* big_list() const { return keys_out; }   // crowded-cell list reuses keys_out (unused by the counting sort)
     size_t sort_tmp_bytes = 0;
     char* stage = nullptr;           // capacity * 8 bytes
@@ -121,6 +123,7 @@ int pst_option(pst_ctx* ctx, const char* name, int dflt = 0);
 // stage implementations (one per .cu)
 pst_status pst_nnps_build(pst_ctx* ctx);                                 // nnps.cu
 pst_status pst_nnps_alloc(pst_ctx* ctx);
+pst_status pst_scan_exclusive(pst_ctx* ctx, int32_t* a, int m);        // in place, m entries (nnps.cu)
 pst_status pst_resolve_history(pst_ctx* ctx);   // run the deferred k_remap_history, if any
 pst_status pst_nnps_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size_t cap, size_t* n_pairs);
 pst_status pst_reorder_upload(pst_ctx* ctx, PstArray* a, int row, size_t n);   // stage -> array (by id)
