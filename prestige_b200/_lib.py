@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprestige_b200.so")
+# PRESTIGE_B200_LIB selects another build of the same library (kernel A/B experiments); never a CPU path
+LIB_PATH = os.environ.get("PRESTIGE_B200_LIB") or os.path.join(_HERE, "libprestige_b200.so")
 
 PST_OK, PST_EINVAL, PST_ENOMEM, PST_ECUDA, PST_ENCCL, PST_EOVERFLOW, PST_ESTATE = range(7)
 STATUS_NAMES = ["PST_OK", "PST_EINVAL", "PST_ENOMEM", "PST_ECUDA", "PST_ENCCL", "PST_EOVERFLOW", "PST_ESTATE"]

@@ -176,7 +176,7 @@ void pst_destroy(pst_ctx* ctx) {
     pst_comm_destroy(ctx);
     for (auto& a : ctx->arrays) { cudaFree(a.buf[0]); if (a.buf[1]) cudaFree(a.buf[1]); }
     cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
-    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->stage); cudaFree(ctx->d_flags);
+    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->stage); cudaFree(ctx->d_flags);
     cudaFree(ctx->d_counters);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);

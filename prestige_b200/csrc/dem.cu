@@ -150,37 +150,51 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
 // Coupled SPH-DEM contexts: fluid particles share the (SPH-sized) cells, so a sphere's 27-cell stencil holds ~370
 // candidates of which only the non-fluid ones can be contact partners, and only ~1 thread in 10 is a sphere.  Each
 // contact pass therefore first compacts the NON-FLUID particles of the sorted order (owned + ghosts):
-//   k_nf_flags  pos[e] = (tag != 0), e = index - lo; also zeroes the outputs of the owned particles that are not spheres
+//   k_nf_clear  zero the force rows the PREVIOUS pass wrote (its compacted list is still there): the output arrays are
+//               not permuted by a re-sort, so this keeps "rows of non-spheres are zero" without touching all N rows
+//   k_nf_flags  pos[e] = (tag != 0), e = index - lo
 //   scan        exclusive, in place (nnps.cu): pos[e] = number of non-fluid particles before e, pos[hi - lo] = their total
-//   k_nf_fill   idx[pos[e]] = index
+//   k_nf_fill   idx[pos[e]] = index, rec[pos[e]] = (x, y, z, rad): the contact TEST then streams 32-byte records that
+//               are contiguous along a compacted run instead of four scattered 8-byte gathers per candidate
 // Because the compaction keeps the sorted order, a cell range [b, e) of the cell table maps to the contiguous range
 // [pos[b], pos[e]) of idx: the contact kernel runs one thread per compacted entry (full warps of spheres) and scans
 // compacted runs (no fluid candidates at all).
 struct NfArgs {
     const int32_t* pos;   // hi - lo + 1 entries
     const int32_t* idx;
+    const void* rec;      // 4 reals per compacted entry: x y z rad
     int lo, hi;           // extended index range [-n_ghost_l, n + n_ghost_r)
 };
 
 template <class R>
-__global__ void __launch_bounds__(256) k_nf_flags(int lo, int hi, int n, const int32_t* __restrict__ tag, int32_t* __restrict__ pos,
+__global__ void __launch_bounds__(256) k_nf_clear(const int32_t* __restrict__ old_total, const int32_t* __restrict__ idx, int n,
                                                   R* __restrict__ fx, R* __restrict__ fy, R* __restrict__ fz, R* __restrict__ tx,
-                                                  R* __restrict__ ty, R* __restrict__ tz, int32_t* __restrict__ hn_out) {
-    const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > hi) return;
-    if (s == hi) { pos[s - lo] = 0; return; }
-    const int t = tag[s];
-    pos[s - lo] = t != 0;
-    if (s >= 0 && s < n && t != 2) {
-        fx[s] = fy[s] = fz[s] = tx[s] = ty[s] = tz[s] = (R)0;
-        hn_out[s] = 0;
-    }
+                                                  R* __restrict__ ty, R* __restrict__ tz) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *old_total) return;
+    const int s = idx[t];
+    if (s >= 0 && s < n) fx[s] = fy[s] = fz[s] = tx[s] = ty[s] = tz[s] = (R)0;
 }
 
-__global__ void __launch_bounds__(256) k_nf_fill(int lo, int hi, const int32_t* __restrict__ tag, const int32_t* __restrict__ pos,
-                                                 int32_t* __restrict__ idx) {
+__global__ void __launch_bounds__(256) k_nf_flags(int lo, int hi, const int32_t* __restrict__ tag, int32_t* __restrict__ pos) {
     const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < hi && tag[s] != 0) idx[pos[s - lo]] = s;
+    if (s > hi) return;
+    pos[s - lo] = s < hi && tag[s] != 0;
+}
+
+template <class R>
+__global__ void __launch_bounds__(256) k_nf_fill(int lo, int hi, const int32_t* __restrict__ tag, const int32_t* __restrict__ pos,
+                                                 const R* __restrict__ x, const R* __restrict__ y, const R* __restrict__ z,
+                                                 const R* __restrict__ rad, int32_t* __restrict__ idx, R* __restrict__ rec,
+                                                 int32_t* __restrict__ total_copy) {
+    const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == hi) *total_copy = pos[hi - lo];      // survives the next pass's scan: k_nf_clear reads it
+    if (s < hi && tag[s] != 0) {
+        const int q = pos[s - lo];
+        idx[q] = s;
+        R* r = rec + 4 * (size_t)q;
+        r[0] = x[s]; r[1] = y[s]; r[2] = z[s]; r[3] = rad[s];
+    }
 }
 
 // linear keys: (1) all 18 run bounds are fetched at once, (2) the contact TEST runs over the candidates four
@@ -190,10 +204,12 @@ __global__ void __launch_bounds__(256) k_nf_fill(int lo, int hi, const int32_t* 
 template <class R, bool NF>
 __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A, NfArgs F) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int own = s;                                        // NF: this thread's compacted index
     if (NF) {
         if (s >= F.pos[F.hi - F.lo]) return;
         s = F.idx[s];
-        if (s < 0 || s >= A.n || A.tag[s] != 2) return;      // ghosts and boundaries are partners only
+        if (s < 0 || s >= A.n) return;                        // ghosts are partners only
+        if (A.tag[s] != 2) { dem_finish<R>(C, A, s, 0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0); return; }   // boundaries too
     } else {
         if (s >= A.n) return;
         if (A.tag && A.tag[s] != 2) { dem_finish<R>(C, A, s, 0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0); return; }
@@ -221,22 +237,26 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
     for (int k = 0; k < 9; ++k) {
         for (int j0 = rb[k]; j0 < re[k]; j0 += 4) {
             R r2[4], rs[4];
-            int tg[4];
-#pragma unroll
-            int jj[4];
+            int tg[4], jj[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int q = min(j0 + t, re[k] - 1);
-                const int j = NF ? F.idx[q] : q;
-                jj[t] = j;
-                r2[t] = dist2<3, R>(xi - A.x[j], yi - A.y[j], zi - A.z[j]);
-                rs[t] = add_rn(ri, A.rad[j]);
-                tg[t] = (!NF && A.tag) ? A.tag[j] : 1;
+                jj[t] = q;
+                if (NF) {
+                    const R* r = reinterpret_cast<const R*>(F.rec) + 4 * (size_t)q;
+                    r2[t] = dist2<3, R>(xi - r[0], yi - r[1], zi - r[2]);
+                    rs[t] = add_rn(ri, r[3]);
+                    tg[t] = 1;
+                } else {
+                    r2[t] = dist2<3, R>(xi - A.x[q], yi - A.y[q], zi - A.z[q]);
+                    rs[t] = add_rn(ri, A.rad[q]);
+                    tg[t] = A.tag ? A.tag[q] : 1;
+                }
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int j = NF ? jj[t] : j0 + t;
-                if (j0 + t < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != s && tg[t] != 0) {
+                const int j = NF ? jj[t] : j0 + t;            // NF: compacted index, mapped to the particle index below
+                if (j0 + t < re[k] && r2[t] < mul_rn(rs[t], rs[t]) && r2[t] > (R)0 && j != (NF ? own : s) && tg[t] != 0) {
                     if (nh < kHits) hits[nh] = j;
                     ++nh;
                 }
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
     R fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     int cnt = 0;
     for (int h = 0; h < min(nh, kHits); ++h)
-        dem_contact<R>(C, A, s, hits[h], xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
+        dem_contact<R>(C, A, s, NF ? F.idx[hits[h]] : hits[h], xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
     if (nh > kHits) cnt = nh;          // more contacts than can ever be stored: reported as overflow below
     dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
 }
@@ -306,21 +326,33 @@ pst_status launch_dem(pst_ctx* ctx) {
     A.stride = ctx->capacity + 2 * ctx->ghost_cap;
     A.n = (int)ctx->n;
     const int variant = MORTON ? 0 : pst_option(ctx, "dem_kernel", ctx->coupled ? 2 : 1);
-    NfArgs F{nullptr, nullptr, 0, 0};
+    NfArgs F{nullptr, nullptr, nullptr, 0, 0};
+    if (!(variant == 2 && ctx->coupled)) ctx->nf_dirty = true;
     if (variant == 0) {
         PST_LAUNCH(ctx, (k_dem_forces_generic<R, MORTON>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A);
     } else if (variant == 2 && ctx->coupled) {
         // compact the non-fluid particles (owned + ghosts), then one thread per compacted entry
         const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r, m = hi - lo + 1;
+        const size_t cap = ctx->capacity + 2 * ctx->ghost_cap + 2;
+        const size_t row = (ctx->capacity + 2 * ctx->ghost_cap) * sizeof(R);
         if (!ctx->nf_pos) {
-            const size_t cap = ctx->capacity + 2 * ctx->ghost_cap + 2;
-            if (cudaMalloc((void**)&ctx->nf_pos, cap * 4) != cudaSuccess || cudaMalloc((void**)&ctx->nf_idx, cap * 4) != cudaSuccess)
+            if (cudaMalloc((void**)&ctx->nf_pos, (cap + 1) * 4) != cudaSuccess || cudaMalloc((void**)&ctx->nf_idx, cap * 4) != cudaSuccess ||
+                cudaMalloc((void**)&ctx->nf_rec, cap * 4 * sizeof(R)) != cudaSuccess)
                 return pst_fail(ctx, PST_ENOMEM, "non-fluid compaction buffers");
         }
-        PST_LAUNCH(ctx, k_nf_flags<R>, blocks_for(m, 256), 256, 0, lo, hi, A.n, A.tag, ctx->nf_pos, A.fx, A.fy, A.fz, A.tx, A.ty, A.tz, A.hn_out);
+        if (ctx->nf_dirty) {   // no usable previous list (first pass, or another kernel variant wrote the rows): zero them all once
+            R* const rows[6] = {A.fx, A.fy, A.fz, A.tx, A.ty, A.tz};
+            for (R* a : rows) PST_CUDA(ctx, cudaMemsetAsync(a - ctx->ghost_cap, 0, row, ctx->stream));
+            PST_CUDA(ctx, cudaMemsetAsync(ctx->nf_pos + cap, 0, 4, ctx->stream));
+            ctx->nf_dirty = false;
+        }
+        int32_t* total_copy = ctx->nf_pos + cap;
+        PST_LAUNCH(ctx, k_nf_clear<R>, blocks_for(cap, 256), 256, 0, total_copy, ctx->nf_idx, (int)ctx->capacity, A.fx, A.fy, A.fz, A.tx, A.ty, A.tz);
+        PST_CUDA(ctx, cudaMemsetAsync(A.hn_out - ctx->ghost_cap, 0, (ctx->capacity + 2 * ctx->ghost_cap) * 4, ctx->stream));
+        PST_LAUNCH(ctx, k_nf_flags, blocks_for(m, 256), 256, 0, lo, hi, A.tag, ctx->nf_pos);
         PST_TRY(pst_scan_exclusive(ctx, ctx->nf_pos, m));
-        PST_LAUNCH(ctx, k_nf_fill, blocks_for(m, 256), 256, 0, lo, hi, A.tag, ctx->nf_pos, ctx->nf_idx);
-        F = NfArgs{ctx->nf_pos, ctx->nf_idx, lo, hi};
+        PST_LAUNCH(ctx, k_nf_fill<R>, blocks_for(m, 256), 256, 0, lo, hi, A.tag, ctx->nf_pos, A.x, A.y, A.z, A.rad, ctx->nf_idx, (R*)ctx->nf_rec, total_copy);
+        F = NfArgs{ctx->nf_pos, ctx->nf_idx, ctx->nf_rec, lo, hi};
         PST_LAUNCH(ctx, (k_dem_forces<R, true>), blocks_for(m, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
     } else {
         PST_LAUNCH(ctx, (k_dem_forces<R, false>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);

@@ -65,6 +65,8 @@ struct pst_ctx {
     int32_t* scan_sums = nullptr;    // tile sums of the count scan (counting sort)
     size_t scan_sums_cap = 0;        // entries
     int32_t *nf_pos = nullptr, *nf_idx = nullptr;   // coupled contexts: compacted non-fluid particles of the sorted order (dem.cu)
+    void* nf_rec = nullptr;                         // their (x, y, z, rad) records
+    bool nf_dirty = true;                           // force rows of non-spheres are not known to be zero
     uint32_t* big_list() const { return keys_out; }   // crowded-cell list reuses keys_out (unused by the counting sort)
     size_t sort_tmp_bytes = 0;
     char* stage = nullptr;           // capacity * 8 bytes

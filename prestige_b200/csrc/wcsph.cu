@@ -389,19 +389,24 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
                 const bool v1 = k + 1 < cnt;
                 const int j0 = __float_as_int(s_p4[my_list[k * NT]].w);
                 const int j1 = v1 ? __float_as_int(s_p4[my_list[(k + 1) * NT]].w) : j0;
-                const R dx0 = I.x - A.x[j0], dy0 = I.y - A.y[j0], dz0 = DIM == 3 ? I.z - A.z[j0] : (R)0;
-                const R dx1 = I.x - A.x[j1], dy1 = I.y - A.y[j1], dz1 = DIM == 3 ? I.z - A.z[j1] : (R)0;
+#if defined(PST_EXP_SMEM)    // timing experiment only (wrong results): the 9 gathers come from shared memory
+                auto LD = [&](const R*, int j, int f) -> R { return (R)reinterpret_cast<const double*>(s_p4)[(j * 9 + f) & 2047]; };
+#else
+                auto LD = [&](const R* arr, int j, int) -> R { return arr[j]; };
+#endif
+                const R dx0 = I.x - LD(A.x, j0, 0), dy0 = I.y - LD(A.y, j0, 1), dz0 = DIM == 3 ? I.z - LD(A.z, j0, 2) : (R)0;
+                const R dx1 = I.x - LD(A.x, j1, 0), dy1 = I.y - LD(A.y, j1, 1), dz1 = DIM == 3 ? I.z - LD(A.z, j1, 2) : (R)0;
                 R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
                 const bool in0 = r20 < I.rc2 && r20 > (R)0;            // the exact test (the set is defined here)
                 const bool in1 = v1 && r21 < I.rc2 && r21 > (R)0;
                 r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
-                R m0 = in0 ? A.m[j0] : (R)0, m1 = in1 ? A.m[j1] : (R)0;
+                R m0 = in0 ? LD(A.m, j0, 3) : (R)0, m1 = in1 ? LD(A.m, j1, 3) : (R)0;
                 if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
                     m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
                     m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
                 }
-                pair_body<R, DIM, CONT, MOM>(C, I, dx0, dy0, dz0, r20, A.u[j0], A.v[j0], DIM == 3 ? A.w[j0] : (R)0, A.rho[j0], m0, A.por2[j0], a);
-                pair_body<R, DIM, CONT, MOM>(C, I, dx1, dy1, dz1, r21, A.u[j1], A.v[j1], DIM == 3 ? A.w[j1] : (R)0, A.rho[j1], m1, A.por2[j1], a2);
+                pair_body<R, DIM, CONT, MOM>(C, I, dx0, dy0, dz0, r20, LD(A.u, j0, 4), LD(A.v, j0, 5), DIM == 3 ? LD(A.w, j0, 6) : (R)0, LD(A.rho, j0, 7), m0, LD(A.por2, j0, 8), a);
+                pair_body<R, DIM, CONT, MOM>(C, I, dx1, dy1, dz1, r21, LD(A.u, j1, 4), LD(A.v, j1, 5), DIM == 3 ? LD(A.w, j1, 6) : (R)0, LD(A.rho, j1, 7), m1, LD(A.por2, j1, 8), a2);
             }
             if (__all_sync(0xffffffffu, done)) break;
         }
