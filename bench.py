@@ -308,7 +308,7 @@ def main():
             raise SystemExit("multi-GPU is implemented for the wcsph3d_10m (weak) and coupled3d_* (strong) slab workloads")
         lo[0], hi[0] = slab
         ny_p, nz_p = block.meta["lattice"][1], block.meta["lattice"][2]
-        ghost_cap = int(2.0 * ny_p * (nz_p + 3) * 3)
+        ghost_cap = int(1.1 * ny_p * (nz_p + 3) * 3)    # a cell layer holds at most 3 lattice planes; also the halo window size
     cap = int(n * 1.02) + 1024
     ctx = pb.Context(dim=block.dim, lo=lo, hi=hi, cell_size=block.cell_size, capacity=cap, real=real, physics=block.physics,
                      key=args.key, max_contacts=block.max_contacts, device=local_rank, ghost_capacity=ghost_cap)

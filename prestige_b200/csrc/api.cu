@@ -203,6 +203,15 @@ static pst_status check_flags(pst_ctx* ctx) {
         PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
         return pst_fail(ctx, PST_EOVERFLOW, "a particle has %d contacts > max_contacts = %d", worst, ctx->cfg.max_contacts);
     }
+    if (ctx->h_flags[4]) {
+        PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
+        return pst_fail(ctx, PST_ENCCL, "peer-memory halo: a slab neighbour did not publish its edge layers in time");
+    }
+    if (ctx->h_flags[2]) {
+        const int need = ctx->h_flags[3];
+        PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
+        return pst_fail(ctx, PST_ENOMEM, "a ghost layer of %d particles exceeds ghost_capacity %llu", need, (unsigned long long)ctx->ghost_cap);
+    }
     return PST_OK;
 }
 
@@ -317,6 +326,7 @@ pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     ctx->n = n;
     ctx->n_ghost_l = ctx->n_ghost_r = 0;
+    ctx->ghost_exact = true;
     ctx->ordered = false;
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;
@@ -331,7 +341,11 @@ pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
 pst_status pst_get_count(pst_ctx* ctx, uint64_t* n_owned, uint64_t* n_ghost) {
     if (!ctx) return PST_EINVAL;
     if (n_owned) *n_owned = ctx->n;
-    if (n_ghost) *n_ghost = (uint64_t)(ctx->n_ghost_l + ctx->n_ghost_r);
+    if (n_ghost) {
+        int64_t nl = 0, nr = 0;
+        PST_TRY(pst_ghost_counts(ctx, &nl, &nr));
+        *n_ghost = (uint64_t)(nl + nr);
+    }
     return PST_OK;
 }
 
@@ -507,8 +521,12 @@ pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value) {
     if (s == "nx") { *value = ctx->grid.n[0]; return PST_OK; }
     if (s == "ny") { *value = ctx->grid.n[1]; return PST_OK; }
     if (s == "nz") { *value = ctx->grid.n[2]; return PST_OK; }
-    if (s == "n_ghost_l") { *value = (double)ctx->n_ghost_l; return PST_OK; }
-    if (s == "n_ghost_r") { *value = (double)ctx->n_ghost_r; return PST_OK; }
+    if (s == "n_ghost_l" || s == "n_ghost_r") {
+        int64_t nl = 0, nr = 0;
+        PST_TRY(pst_ghost_counts(ctx, &nl, &nr));
+        *value = (double)(s == "n_ghost_l" ? nl : nr);
+        return PST_OK;
+    }
     if (s == "ordered") { *value = ctx->ordered; return PST_OK; }
     if (s == "particles_per_occupied_cell") { *value = pst_param(ctx, "_ppc", 0.0); return PST_OK; }
     if (s == "contacts_total") {  // sum of hist_n over owned particles

@@ -12,6 +12,8 @@
 // already loaded a libnccl (e.g. torch's bundled one) shares it.
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "pst_internal.h"
@@ -72,10 +74,23 @@ NcclApi* nccl_api() {
 struct PstComm {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
-    int32_t* d_counts = nullptr;   // [0..1] my send counts (left, right), [2..3] received counts
-    int32_t* h_counts = nullptr;   // pinned: [0..3] as above, [4..7] boundary cell_start values
+    int32_t* d_counts = nullptr;   // 16 ints: old path [0..1] my send counts (left, right), [2..3] received counts;
+                                   // migration [4..6] left neighbour's (n_stay, n_stay+nL, n), [8..10] right neighbour's;
+                                   // windowed halo [12] nL, [13] nR (ghost counts, device-side only)
+    int32_t* h_counts = nullptr;   // pinned, 16 ints: mirrors of the above as needed
     int32_t* d_tab_l = nullptr;    // received cell-table slice for the left / right ghost layer
     int32_t* d_tab_r = nullptr;
+    // windowed halo: one packed message per neighbour and direction = W elements of every ghost array + the table slice
+    char* send_buf[2] = {nullptr, nullptr};   // [0] to the left, [1] to the right
+    char* recv_buf[2] = {nullptr, nullptr};   // [0] from the left, [1] from the right
+    size_t msg_bytes = 0;
+    // peer-memory halo (halo_impl = 2): my RECEIVE buffers are double-buffered by step parity and exported with
+    // cudaIpc; each neighbour's pack kernel STORES its window straight into them over NVLink (stores are fire-and-forget,
+    // remote loads would be latency-bound) and then raises the epoch word at the end of the buffer.
+    char* p2p_send[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][parity]: MY receive buffers ([0] filled by the left neighbour)
+    char* p2p_peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [0] = the left neighbour's buffer for what comes from ITS right (= me), [1] likewise
+    size_t p2p_bytes = 0;
+    int epoch = 0;
 };
 
 #define PST_NCCL(ctx, expr)                                                                                  \
@@ -92,6 +107,114 @@ __global__ void k_rebase_table(int count, const int32_t* __restrict__ recv, int 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < count) cell_start[t] = recv[t] - recv[0] + base;
 }
+constexpr int kMaxHalo = 20;
+struct HaloList {
+    char* arr[kMaxHalo];       // owned-view base of each ghost array
+    size_t off[kMaxHalo + 1];  // byte offset of each array's window inside a packed message; [n_arr] = the table slice
+    int esize[kMaxHalo];
+    int n_arr;
+};
+
+// Pack both edge windows: blockIdx.y = array (n_arr = the cell-table slice of the edge layer), blockIdx.z = side.
+// Left window = elements [0, W), right window = [n - W, n) of every array.
+// `exact`: only the elements of the edge layer itself are written (head of the left window, tail of the right one).
+__global__ void __launch_bounds__(256) k_halo_pack(HaloList L, int W, int n, int layer, const int32_t* __restrict__ cell_start, size_t kL0,
+                                                   size_t kR0, char* __restrict__ buf_l, char* __restrict__ buf_r, int has_l, int has_r, int exact) {
+    const int side = blockIdx.z, a = blockIdx.y;
+    if (side == 0 ? !has_l : !has_r) return;
+    char* buf = side == 0 ? buf_l : buf_r;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == L.n_arr) {
+        if (t <= layer) reinterpret_cast<int32_t*>(buf + L.off[a])[t] = cell_start[(side == 0 ? kL0 : kR0) + t];
+        return;
+    }
+    if (t >= W) return;
+    if (exact) {
+        const size_t k0 = side == 0 ? kL0 : kR0;
+        const int ext = cell_start[k0 + layer] - cell_start[k0];
+        if (side == 0 ? t >= ext : t < W - ext) return;
+    }
+    const ptrdiff_t s = side == 0 ? t : (ptrdiff_t)n - W + t;
+    if (L.esize[a] == 8) reinterpret_cast<unsigned long long*>(buf + L.off[a])[t] = reinterpret_cast<const unsigned long long*>(L.arr[a])[s];
+    else reinterpret_cast<uint32_t*>(buf + L.off[a])[t] = reinterpret_cast<const uint32_t*>(L.arr[a])[s];
+}
+
+// Unpack the received windows into the ghost regions -- the left neighbour's END-aligned into [-W, 0), the right
+// neighbour's START-aligned into [n, n + W) -- and splice the (rebased) table slices into the cell table.
+__global__ void __launch_bounds__(256) k_halo_unpack(HaloList L, int W, int n, int layer, int32_t* __restrict__ cell_start, size_t kR1,
+                                                     const char* __restrict__ buf_l, const char* __restrict__ buf_r, int has_l, int has_r,
+                                                     int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
+    const int side = blockIdx.z, a = blockIdx.y;
+    if (side == 0 ? !has_l : !has_r) return;
+    const char* buf = side == 0 ? buf_l : buf_r;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == L.n_arr) {
+        const int32_t* recv = reinterpret_cast<const int32_t*>(buf + L.off[a]);
+        const int ext = recv[layer] - recv[0];             // the layer's true particle count
+        if (side == 0) { if (t < layer) cell_start[t] = recv[t] - recv[0] - ext; }
+        else if (t <= layer) cell_start[kR1 + t] = recv[t] - recv[0] + n;
+        if (t == 0) { counts[12 + side] = ext; if (ext > W) { atomicExch(&flags[2], 1); atomicMax(&flags[3], ext); } }
+        return;
+    }
+    if (t >= W) return;
+    const ptrdiff_t d = side == 0 ? (ptrdiff_t)t - W : (ptrdiff_t)n + t;
+    if (L.esize[a] == 8) reinterpret_cast<unsigned long long*>(L.arr[a])[d] = reinterpret_cast<const unsigned long long*>(buf + L.off[a])[t];
+    else reinterpret_cast<uint32_t*>(L.arr[a])[d] = reinterpret_cast<const uint32_t*>(buf + L.off[a])[t];
+}
+
+// ---- peer-memory variant -------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// after the pack kernel (stream order): make the windows visible system-wide, then raise the epoch words
+__global__ void k_halo_publish(int* flag_l, int* flag_r, int epoch) {
+    __threadfence_system();
+    if (flag_l) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag_l), "r"(epoch) : "memory");
+    if (flag_r) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag_r), "r"(epoch) : "memory");
+}
+
+// Wait + unpack in one kernel: every CTA waits until the neighbour has raised this step's epoch word at the end of my
+// receive buffer, reads the table slice to learn the layer's true particle count, and copies only that many elements of
+// every array into my ghost region -- the left neighbour's layer is the TAIL of its right window and lands on
+// [-ext, 0), the right neighbour's the HEAD of its left window and lands on [n, n + ext).  No NCCL, no host round trip.
+__global__ void __launch_bounds__(256) k_halo_pull(HaloList L, int W, int n, int layer, int32_t* __restrict__ cell_start, size_t kR1,
+                                                   const char* __restrict__ peer_l, const char* __restrict__ peer_r, size_t flag_off,
+                                                   int epoch, int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
+    const int side = blockIdx.z, a = blockIdx.y;
+    const char* buf = side == 0 ? peer_l : peer_r;
+    if (!buf) return;
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        const int* flag = reinterpret_cast<const int*>(buf + flag_off);
+        const long long t0 = clock64();
+        int seen = ld_acquire_sys(flag);
+        while (seen < epoch && clock64() - t0 < 6000000000ll && *(volatile int*)&flags[4] == 0) { __nanosleep(200); seen = ld_acquire_sys(flag); }
+        ok = seen >= epoch;
+        if (!ok) atomicExch(&flags[4], 1);        // neighbour never published: reported as PST_ENCCL at the next sync
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t* recv = reinterpret_cast<const int32_t*>(buf + L.off[L.n_arr]);
+    const int r0 = __ldcg(recv), ext = __ldcg(recv + layer) - r0;          // the layer's true particle count
+    if (a == L.n_arr) {
+        if (side == 0) { if (t < layer) cell_start[t] = __ldcg(recv + t) - r0 - ext; }
+        else if (t <= layer) cell_start[kR1 + t] = __ldcg(recv + t) - r0 + n;
+        if (t == 0) { counts[12 + side] = ext; if (ext > W) { atomicExch(&flags[2], 1); atomicMax(&flags[3], ext); } }
+        return;
+    }
+    const int m = min(ext, W);
+    if (t >= m) return;
+    const ptrdiff_t src = side == 0 ? (ptrdiff_t)W - m + t : t;
+    const ptrdiff_t dst = side == 0 ? (ptrdiff_t)t - m : (ptrdiff_t)n + t;
+    // loads bypass L1 (__ldcg): the neighbour rewrites this buffer over NVLink every second step
+    if (L.esize[a] == 8) reinterpret_cast<unsigned long long*>(L.arr[a])[dst] = __ldcg(reinterpret_cast<const unsigned long long*>(buf + L.off[a]) + src);
+    else reinterpret_cast<uint32_t*>(L.arr[a])[dst] = __ldcg(reinterpret_cast<const uint32_t*>(buf + L.off[a]) + src);
+}
+
 std::vector<PstArray*> ghost_arrays(pst_ctx* ctx) {
     std::vector<PstArray*> v;
     auto add = [&](const char* nm) { if (PstArray* a = pst_find(ctx, nm)) v.push_back(a); };
@@ -153,8 +276,8 @@ extern "C" pst_status pst_comm_init(pst_ctx* ctx, const void* id_bytes, int rank
     PstComm* c = new PstComm();
     c->rank = rank; c->nranks = n_ranks;
     const size_t layer = (size_t)g.n[1] * g.n[2] + 1;
-    if (cudaMalloc((void**)&c->d_counts, 8 * 4) != cudaSuccess || cudaMalloc((void**)&c->d_tab_l, layer * 4) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_tab_r, layer * 4) != cudaSuccess || cudaHostAlloc((void**)&c->h_counts, 8 * 4, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaMalloc((void**)&c->d_counts, 16 * 4) != cudaSuccess || cudaMalloc((void**)&c->d_tab_l, layer * 4) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_tab_r, layer * 4) != cudaSuccess || cudaHostAlloc((void**)&c->h_counts, 16 * 4, cudaHostAllocDefault) != cudaSuccess) {
         delete c;
         return pst_fail(ctx, PST_ENOMEM, "halo buffers");
     }
@@ -172,9 +295,26 @@ pst_status pst_comm_destroy(pst_ctx* ctx) {
     PstComm* c = ctx->comm;
     if (c->comm) nccl_api()->CommDestroy(c->comm);
     cudaFree(c->d_counts); cudaFree(c->d_tab_l); cudaFree(c->d_tab_r);
+    for (int k = 0; k < 2; ++k) { cudaFree(c->send_buf[k]); cudaFree(c->recv_buf[k]); }
+    for (int sd = 0; sd < 2; ++sd)
+        for (int par = 0; par < 2; ++par) {
+            if (c->p2p_peer[sd][par]) cudaIpcCloseMemHandle(c->p2p_peer[sd][par]);
+            cudaFree(c->p2p_send[sd][par]);
+        }
     if (c->h_counts) cudaFreeHost(c->h_counts);
     delete c;
     ctx->comm = nullptr;
+    return PST_OK;
+}
+
+// true ghost counts (the windowed halo keeps them on the device; this synchronises)
+pst_status pst_ghost_counts(pst_ctx* ctx, int64_t* nl, int64_t* nr) {
+    *nl = ctx->n_ghost_l; *nr = ctx->n_ghost_r;
+    if (!ctx->comm || ctx->ghost_exact || (ctx->n_ghost_l == 0 && ctx->n_ghost_r == 0)) return PST_OK;
+    PstComm* c = ctx->comm;
+    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 12, c->d_counts + 12, 2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *nl = c->h_counts[12]; *nr = c->h_counts[13];
     return PST_OK;
 }
 
@@ -194,21 +334,22 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
     NcclApi* api = nccl_api();
     const int left = c->rank > 0 ? c->rank - 1 : -1, right = c->rank + 1 < c->nranks ? c->rank + 1 : -1;
     const size_t nc = ctx->grid.ncells;
-    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 4, ctx->cell_start + nc, 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int n_stay = c->h_counts[4], nL = c->h_counts[5] - c->h_counts[4], nR = c->h_counts[6] - c->h_counts[5];
-    c->h_counts[0] = nL; c->h_counts[1] = nR; c->h_counts[2] = c->h_counts[3] = 0;
-    PST_CUDA(ctx, cudaMemcpyAsync(c->d_counts, c->h_counts, 4 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // The three table entries (n_stay, n_stay + nL, n) go to both neighbours straight from device memory, then ONE
+    // read-back + stream sync tells the host its own split and what arrives (was: sync, count hand-shake, sync).
     PST_NCCL(ctx, api->GroupStart());
-    if (left >= 0) { PST_NCCL(ctx, api->Send(c->d_counts + 0, 4, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 2, 4, ncclInt8, left, c->comm, ctx->stream)); }
-    if (right >= 0) { PST_NCCL(ctx, api->Send(c->d_counts + 1, 4, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 3, 4, ncclInt8, right, c->comm, ctx->stream)); }
+    if (left >= 0) { PST_NCCL(ctx, api->Send(ctx->cell_start + nc, 12, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 4, 12, ncclInt8, left, c->comm, ctx->stream)); }
+    if (right >= 0) { PST_NCCL(ctx, api->Send(ctx->cell_start + nc, 12, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 8, 12, ncclInt8, right, c->comm, ctx->stream)); }
     PST_NCCL(ctx, api->GroupEnd());
-    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 2, c->d_counts + 2, 2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts, ctx->cell_start + nc, 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 4, c->d_counts + 4, 8 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int aL = left >= 0 ? c->h_counts[2] : 0, aR = right >= 0 ? c->h_counts[3] : 0;
+    const int n_stay = c->h_counts[0], nL = c->h_counts[1] - c->h_counts[0], nR = c->h_counts[2] - c->h_counts[1];
+    // what the left neighbour sends me is ITS right-leavers, and vice versa
+    const int aL = left >= 0 ? c->h_counts[6] - c->h_counts[5] : 0, aR = right >= 0 ? c->h_counts[9] - c->h_counts[8] : 0;
     if ((uint64_t)n_stay + aL + aR > ctx->capacity)
         return pst_fail(ctx, PST_ENOMEM, "migration: %d stayers + %d arrivals exceed capacity %llu", n_stay, aL + aR, (unsigned long long)ctx->capacity);
     if (nL + nR + aL + aR > 0) {
+        PST_TRY(pst_resolve_history(ctx));   // contact-history rows travel with their particles: put them in the new order first
         PST_NCCL(ctx, api->GroupStart());
         for (auto& a : ctx->arrays) {
             if (!(a.flags & PST_ARRAY_PERSISTENT)) continue;
@@ -240,6 +381,41 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
     return PST_OK;
 }
 
+// one-time setup of the peer-memory halo: allocate my double-buffered send windows, swap cudaIpc handles with the two
+// slab neighbours (the 64-byte handles travel by ncclSend/ncclRecv, once), map theirs.
+static pst_status p2p_setup(pst_ctx* ctx, size_t bytes, int left, int right) {
+    PstComm* c = ctx->comm;
+    NcclApi* api = nccl_api();
+    if (c->p2p_bytes >= bytes) return PST_OK;
+    if (c->p2p_bytes != 0) return pst_fail(ctx, PST_ESTATE, "peer-memory halo: the message size changed after setup");
+    cudaIpcMemHandle_t mine[2][2], theirs[2][2];
+    std::memset(theirs, 0, sizeof theirs);
+    for (int sd = 0; sd < 2; ++sd)
+        for (int par = 0; par < 2; ++par) {
+            if (cudaMalloc((void**)&c->p2p_send[sd][par], bytes) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "peer-memory halo buffers (%zu bytes)", bytes);
+            PST_CUDA(ctx, cudaMemsetAsync(c->p2p_send[sd][par], 0, bytes, ctx->stream));
+            PST_CUDA(ctx, cudaIpcGetMemHandle(&mine[sd][par], c->p2p_send[sd][par]));
+        }
+    constexpr size_t HB = sizeof(cudaIpcMemHandle_t);
+    char* d_h = nullptr;                               // [0..1] mine for the left, [2..3] mine for the right, [4..5] from left, [6..7] from right
+    PST_CUDA(ctx, cudaMalloc((void**)&d_h, 8 * HB));
+    PST_CUDA(ctx, cudaMemcpyAsync(d_h, mine, 4 * HB, cudaMemcpyHostToDevice, ctx->stream));
+    PST_NCCL(ctx, api->GroupStart());
+    if (left >= 0) { PST_NCCL(ctx, api->Send(d_h, 2 * HB, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(d_h + 4 * HB, 2 * HB, ncclInt8, left, c->comm, ctx->stream)); }
+    if (right >= 0) { PST_NCCL(ctx, api->Send(d_h + 2 * HB, 2 * HB, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(d_h + 6 * HB, 2 * HB, ncclInt8, right, c->comm, ctx->stream)); }
+    PST_NCCL(ctx, api->GroupEnd());
+    PST_CUDA(ctx, cudaMemcpyAsync(theirs, d_h + 4 * HB, 4 * HB, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    // what the left neighbour sent me are the handles of ITS windows for its RIGHT neighbour (= me), and vice versa
+    for (int par = 0; par < 2; ++par) {
+        if (left >= 0) PST_CUDA(ctx, cudaIpcOpenMemHandle((void**)&c->p2p_peer[0][par], theirs[0][par], cudaIpcMemLazyEnablePeerAccess));
+        if (right >= 0) PST_CUDA(ctx, cudaIpcOpenMemHandle((void**)&c->p2p_peer[1][par], theirs[1][par], cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p_bytes = bytes;
+    return PST_OK;
+}
+
 extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
     if (!ctx) return PST_EINVAL;
     if (!ctx->comm) return pst_fail(ctx, PST_ESTATE, "no communicator attached (pst_comm_init)");
@@ -252,6 +428,85 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
     const int left = c->rank > 0 ? c->rank - 1 : -1, right = c->rank + 1 < c->nranks ? c->rank + 1 : -1;
     const size_t kL0 = (size_t)g.cx_lo * layer, kL1 = kL0 + layer;           // my first owned layer
     const size_t kR0 = (size_t)g.cx_hi * layer, kR1 = kR0 + layer;           // my last owned layer
+    // 2 = peer memory (default), 1 = one packed NCCL message per neighbour, 0 = exact per-array NCCL exchange with count hand-shake
+    static const int impl_default = std::getenv("PST_HALO_IMPL") ? std::atoi(std::getenv("PST_HALO_IMPL")) : 2;
+    const int impl = pst_option(ctx, "halo_impl", impl_default);
+    if (impl == 1 || impl == 2) {
+        // ---- windowed exchange: no count hand-shake, no host round trip, ONE NCCL group.
+        // My first owned layer starts at index 0 and my last one ends at n, so fixed windows of W = ghost_capacity
+        // elements -- [0, W) to the left, [n - W, n) to the right -- always contain the edge layers.  The left
+        // neighbour's window is received END-aligned into [-W, 0), the right neighbour's START-aligned into [n, n + W):
+        // the layers land exactly where the cell table expects them, whatever their true size; the surplus is never
+        // referenced (the table slices that travel alongside carry the true extents, rebased on the device).
+        // All windows of one direction travel as ONE packed message (a pack kernel, one ncclSend/ncclRecv per
+        // neighbour, an unpack kernel): 14 + 1 separate sends per neighbour cost ~0.5 ms of NCCL per-operation overhead.
+        const int W = (int)ctx->ghost_cap, n = (int)ctx->n;
+        HaloList L;
+        L.n_arr = 0;
+        size_t off = 0;
+        std::vector<PstArray*> ga = ghost_arrays(ctx);
+        std::stable_sort(ga.begin(), ga.end(), [](PstArray* x, PstArray* y) { return x->esize > y->esize; });   // 8-byte arrays first: alignment
+        if ((int)ga.size() > kMaxHalo) return pst_fail(ctx, PST_EINVAL, "too many ghost arrays");
+        for (PstArray* a : ga) {
+            L.arr[L.n_arr] = pst_ptr<char>(ctx, a);
+            L.esize[L.n_arr] = (int)a->esize;
+            L.off[L.n_arr] = off;
+            off += (size_t)W * a->esize;
+            ++L.n_arr;
+        }
+        L.off[L.n_arr] = off;
+        const size_t msg = off + ((size_t)layer + 1) * 4;
+        const int span = std::max(W, layer + 1);
+        const dim3 grid((unsigned)((span + 255) / 256), (unsigned)(L.n_arr + 1), 2);
+        if (impl == 2) {
+            // ---- peer memory: the pack kernel stores this step's edge layers into the neighbours' parity buffers over
+            // NVLink, a one-thread kernel raises the epoch words there, the unpack kernel waits for MY buffers' epoch
+            const size_t flag_off = (msg + 15) & ~(size_t)15;
+            PST_TRY(p2p_setup(ctx, flag_off + 16, left, right));
+            const int e = ++c->epoch, par = e & 1;
+            PST_LAUNCH(ctx, k_halo_pack, grid, 256, 0, L, W, n, layer, ctx->cell_start, kL0, kR0, c->p2p_peer[0][par], c->p2p_peer[1][par], left >= 0, right >= 0, 1);
+            PST_LAUNCH(ctx, k_halo_publish, 1, 1, 0, left >= 0 ? (int*)(c->p2p_peer[0][par] + flag_off) : nullptr,
+                       right >= 0 ? (int*)(c->p2p_peer[1][par] + flag_off) : nullptr, e);
+            PST_CUDA(ctx, cudaMemsetAsync(c->d_counts + 12, 0, 2 * 4, ctx->stream));
+            PST_LAUNCH(ctx, k_halo_pull, grid, 256, 0, L, W, n, layer, ctx->cell_start, kR1, left >= 0 ? (const char*)c->p2p_send[0][par] : nullptr,
+                       right >= 0 ? (const char*)c->p2p_send[1][par] : nullptr, flag_off, e, c->d_counts, ctx->d_flags);
+            ctx->n_ghost_l = left >= 0 ? W : 0;
+            ctx->n_ghost_r = right >= 0 ? W : 0;
+            ctx->ghost_exact = false;
+            ctx->eos_valid = false;
+            return PST_OK;
+        }
+        if (c->msg_bytes < msg) {
+            PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int k = 0; k < 2; ++k) {
+                cudaFree(c->send_buf[k]); cudaFree(c->recv_buf[k]);
+                c->send_buf[k] = c->recv_buf[k] = nullptr;
+                if (cudaMalloc((void**)&c->send_buf[k], msg) != cudaSuccess || cudaMalloc((void**)&c->recv_buf[k], msg) != cudaSuccess)
+                    return pst_fail(ctx, PST_ENOMEM, "halo message buffers (%zu bytes)", msg);
+            }
+            c->msg_bytes = msg;
+        }
+        PST_LAUNCH(ctx, k_halo_pack, grid, 256, 0, L, W, n, layer, ctx->cell_start, kL0, kR0, c->send_buf[0], c->send_buf[1], left >= 0, right >= 0, 0);
+        PST_NCCL(ctx, api->GroupStart());
+        if (left >= 0) {
+            PST_NCCL(ctx, api->Send(c->send_buf[0], msg, ncclInt8, left, c->comm, ctx->stream));
+            PST_NCCL(ctx, api->Recv(c->recv_buf[0], msg, ncclInt8, left, c->comm, ctx->stream));
+        }
+        if (right >= 0) {
+            PST_NCCL(ctx, api->Send(c->send_buf[1], msg, ncclInt8, right, c->comm, ctx->stream));
+            PST_NCCL(ctx, api->Recv(c->recv_buf[1], msg, ncclInt8, right, c->comm, ctx->stream));
+        }
+        PST_NCCL(ctx, api->GroupEnd());
+        PST_CUDA(ctx, cudaMemsetAsync(c->d_counts + 12, 0, 2 * 4, ctx->stream));
+        PST_LAUNCH(ctx, k_halo_unpack, grid, 256, 0, L, W, n, layer, ctx->cell_start, kR1, c->recv_buf[0], c->recv_buf[1], left >= 0, right >= 0,
+                   c->d_counts, ctx->d_flags);
+        // the host only knows bounds: per-particle passes over "owned + ghosts" cover the whole windows
+        ctx->n_ghost_l = left >= 0 ? W : 0;
+        ctx->n_ghost_r = right >= 0 ? W : 0;
+        ctx->ghost_exact = false;
+        ctx->eos_valid = false;
+        return PST_OK;
+    }
     // 1. where do my edge layers start and end?  (4 table entries -> host)
     PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 4, ctx->cell_start + kL0, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 5, ctx->cell_start + kL1, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -307,6 +562,7 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
     }
     ctx->n_ghost_l = nL;
     ctx->n_ghost_r = nR;
+    ctx->ghost_exact = true;
     ctx->eos_valid = false;
     return PST_OK;
 }

@@ -387,6 +387,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     int key_bits = ctx->grid.key_bits;
     while (mig && (1ull << key_bits) < (unsigned long long)nkeys) ++key_bits;
     ctx->n_ghost_l = ctx->n_ghost_r = 0;
+    ctx->ghost_exact = true;
     // occupied-cell count of the PREVIOUS build (read back asynchronously; the very first build waits once)
     if (ctx->stats_pending) {
         PST_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
@@ -449,11 +450,8 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
         for (PstArray* a : moved) a->cur = 1 - a->cur;
         // Contact history: the remap is DEFERRED -- the next contact pass reads each row through vals_out (new -> old
         // index) and writes it back in place of a separate 2 x (28 Z + 4) B/particle copy.  Anything else that needs the
-        // rows in the new order (a second re-sort, a download, migration) resolves the lag first.
-        if (pst_find(ctx, "hist_n")) {
-            if (ctx->comm) { if (ctx->f64) PST_TRY(launch_remap<double>(ctx)); else PST_TRY(launch_remap<float>(ctx)); }
-            else ctx->hist_lag = true;
-        }
+        // rows in the new order (a second re-sort, a download, a migration that moves particles) resolves the lag first.
+        if (pst_find(ctx, "hist_n")) ctx->hist_lag = true;   // (migration resolves it first, and only when particles actually move)
     }
     ctx->ordered = true;
     ctx->nbrs_valid = true;

@@ -55,7 +55,8 @@ struct pst_ctx {
     std::map<std::string, double> params;
     std::map<std::string, int> options;
     uint64_t n = 0;          // owned particles
-    int64_t n_ghost_l = 0, n_ghost_r = 0;
+    int64_t n_ghost_l = 0, n_ghost_r = 0;   // ghost index range [-n_ghost_l, n + n_ghost_r); bounds only when !ghost_exact
+    bool ghost_exact = true;                // false after a windowed halo exchange: the true counts live on the device
     uint64_t capacity = 0, ghost_cap = 0;
     PstGrid grid;
     // neighbour-search scratch
@@ -140,6 +141,7 @@ pst_status pst_dem_integrate(pst_ctx* ctx, double dt);
 pst_status pst_coupled_integrate(pst_ctx* ctx, double dt);                // wcsph.cu
 pst_status pst_comm_destroy(pst_ctx* ctx);                                // halo.cu
 void pst_comm_neighbours(pst_ctx* ctx, int* has_left, int* has_right);
+pst_status pst_ghost_counts(pst_ctx* ctx, int64_t* nl, int64_t* nr);
 pst_status pst_migrate(pst_ctx* ctx, int* arrivals);   // after a build pass with sentinel keys: ship leavers, append arrivals
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,15 @@
+#!/bin/bash
+# 2-GPU check of the peer-memory halo (halo_impl = 2): slab parity tests with it as the default, then A/B bench lines
+mkdir -p gpurun_out
+nvidia-smi topo -m 2>/dev/null | head -6
+echo "== multi-GPU tests, PST_HALO_IMPL=2"; PST_HALO_IMPL=2 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider -x 2>&1 | tail -25
+N=2
+for WL in wcsph3d_10m coupled3d_20m; do
+for IMPL in 1 2; do
+echo "== bench $WL N=$N halo_impl=$IMPL"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --workload $WL --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --opt halo_impl=$IMPL 2> gpurun_out/bench_n$N.err | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('value %.4g ms/step %.3f' % (d['value'], d['ms_per_step']), {k: round(v,3) for k,v in d['roofline']['stage_ms'].items()})
+"; tail -3 gpurun_out/bench_n$N.err | grep -v "OMP_NUM\|\*\*\*\*" | cut -c1-300
+done; done
