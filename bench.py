@@ -62,6 +62,10 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
+# what pst_halo_exchange does by default (csrc/halo.cu: halo_impl option / PST_HALO_IMPL): 2 = peer memory, 1 = packed NCCL, 0 = per-array NCCL
+HALO_DESC = {"2": "peer-memory halo (pack kernel stores into the neighbour's cudaIpc buffer over NVLink, epoch flag, wait+unpack kernel)",
+             "1": "one packed NCCL send/recv message per neighbour", "0": "per-array NCCL send/recv halo with count hand-shake"}.get(
+                 os.environ.get("PST_HALO_IMPL", "2"), "peer-memory halo")
 SLAB_CELLS = 83   # multi-GPU: every rank owns 83 cell layers (0.996 m, ~199.2 lattice planes, ~9.96 M particles)
 
 
@@ -461,7 +465,7 @@ def main():
                 "dtype": args.real, "data": "synthetic",
                 "config": {"workload": args.workload, "particles": n_total, "particles_per_gpu": n_local, "dim": block.dim,
                            "physics": block.physics, "key": args.key, "force_kernel": kern,
-                           "decomposition": (f"{world} x-slabs of the same block, NCCL send/recv halo" if coupled else f"{world} x-slabs of {SLAB_CELLS} cell layers, NCCL send/recv halo") if world > 1 else "single GPU",
+                           "decomposition": (f"{world} x-slabs of the same block, {HALO_DESC}" if coupled else f"{world} x-slabs of {SLAB_CELLS} cell layers, {HALO_DESC}") if world > 1 else "single GPU",
                            "l2": f"no flush needed: state + outputs = {n_local * (b_step) / 1e6:.0f} MB touched per step >> 126 MB L2",
                            "timed": "keys+sort+cell table+permute" + ("+history remap" if block.physics != "wcsph" else "") + ("+halo exchange" if world > 1 else "") + ("+contact kernel" if block.physics == "dem" else "+EOS+fused pair kernel" + ("+contact kernel" if coupled else "")) + "; integrator excluded",
                            "mean_contacts": zbar_total if block.physics != "wcsph" else None,

@@ -1,12 +1,18 @@
-// halo.cu -- multi-GPU slab decomposition along x: ghost-particle exchange with the two slab neighbours
-// by NCCL send/recv over NVLink.  One context = one rank = one GPU.
+// halo.cu -- multi-GPU slab decomposition along x: ghost-particle exchange with the two slab neighbours and
+// particle migration.  One context = one rank = one GPU.
 //
 // Layout trick: with x as the SLOWEST key digit, a rank's outermost owned cell layer is one contiguous
-// range of every sorted array, so there is no pack kernel: ncclSend reads straight out of the sorted
-// arrays, ncclRecv writes straight into the ghost region.  Left ghosts land at indices [-nL, 0),
-// right ghosts at [n, n + nR) of the same allocation, so the whole thing stays ONE monotone index
-// space and the cell table keeps its prefix semantics (cell_start is signed for this reason).
-// The neighbour's cell-table slice for the layer travels with the particles and is rebased on arrival.
+// range of every sorted array.  Left ghosts land at indices [-nL, 0), right ghosts at [n, n + nR) of the same
+// allocation, so the whole thing stays ONE monotone index space and the cell table keeps its prefix semantics
+// (cell_start is signed for this reason).  The neighbour's cell-table slice for the layer travels with the
+// particles and is rebased on arrival.
+//
+// Three exchanges (option halo_impl / PST_HALO_IMPL):
+//   2 (default)  peer memory: k_halo_pack stores the edge layers into the neighbour's cudaIpc receive buffer over
+//                NVLink, k_halo_publish raises an epoch word, k_halo_pull waits for it and unpacks.  No NCCL call and
+//                no host round trip per step.
+//   1            the same fixed-size windows as ONE packed ncclSend/ncclRecv message per neighbour.
+//   0            exact per-array ncclSend/ncclRecv straight out of / into the sorted arrays after a count hand-shake.
 //
 // NCCL is loaded with dlopen at pst_comm_init, so single-GPU users need no NCCL at all and a host that
 // already loaded a libnccl (e.g. torch's bundled one) shares it.
