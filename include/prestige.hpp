@@ -97,6 +97,13 @@ struct dem_contact {
                 "{ (F [i] , T [i] , xi [i] [j]) += spring_dashpot (x_ij , v_ij , w , rad , xi [i] [j]) ; }"};
     }
 };
+// per-particle (no j): sums the force loop's results over the members of each rigid body
+struct body_reduce {
+    static equations::ir::EquationIR ir() {
+        return {"body_reduce", {"x", "y", "z", "m", "body", "fx", "fy", "fz", "tx", "ty", "tz", "au", "av", "aw"}, {"body_force", "body_torque"},
+                "{ body_force [body [i]] += f_total (i) ; body_torque [body [i]] += cross (x [i] - cm [body [i]] , f_total (i)) + t [i] ; }"};
+    }
+};
 
 namespace codegen {
 namespace simple_cpu {
@@ -118,7 +125,7 @@ inline std::string generate_simple_cpu(const equations::fuse::FusedEquations& ir
 namespace b200 {
 // The launch plan for a fused set: the names pst_apply receives, in body order.
 inline std::vector<std::string> generate_b200(const equations::fuse::FusedEquations& ir) {
-    static const std::set<std::string> kernels = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact"};
+    static const std::set<std::string> kernels = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact", "body_reduce"};
     if (ir.names.empty()) throw std::invalid_argument("FusedEquations.names is empty");
     for (const auto& n : ir.names)
         if (!kernels.count(n)) throw std::invalid_argument("no hand-written kernel for equation '" + n + "'");

@@ -132,7 +132,7 @@ PST_API void pst_host_free(void* p);
 /* cell keys -> radix sort -> cell start table -> permute persistent state (+ history remap) */
 PST_API pst_status pst_build_neighbours(pst_ctx* ctx);
 /* fuse(): run the hand-written fused kernel for this equation set, bodies in the given order.
- * Known names: "eq1" | "tait_eos" "continuity" "momentum" | "dem_contact"                     */
+ * Known names: "eq1" | "tait_eos" "continuity" "momentum" | "dem_contact" | "body_reduce"     */
 PST_API pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq);
 /* parity hook: neighbour set (mode 0: r2 < (kfac h_i)^2) or contact set (mode 1: r2 < (R_i+R_j)^2)
  * as stable ids; order unspecified.  *n_pairs is always the true count; PST_EOVERFLOW if > cap. */
@@ -146,6 +146,27 @@ PST_API pst_status pst_integrate(pst_ctx* ctx, double dt);
 PST_API pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value);
 /* select a kernel variant (A/B measurement): name "force_kernel" value 0 = per-particle gather, 1 = tiled */
 PST_API pst_status pst_set_option(pst_ctx* ctx, const char* name, int value);
+
+/* ---- multi-particle rigid bodies in a coupled context (no reference code) ---------------------
+ * A body is the set of tag-2 particles whose persistent i32 array `body` holds its index (-1 = none: the particle is
+ * its own body).  Members keep taking part in the force loop one by one (SPH pairs with fluid, contacts with
+ * non-members); pst_apply({"body_reduce"}) sums their forces to one force and one torque about the centre of mass per
+ * body, and pst_integrate / pst_step advance the bodies (semi-implicit Euler, rotation matrix by Rodrigues' formula)
+ * and set x = X + R r0, v = V + omega x (x - X), spin = omega on every member.  One GPU only (no communicator). */
+/* registers `n_bodies` bodies and the particle arrays body (i32, all -1), bx0 by0 bz0 (body-frame offsets) and bpos
+ * (i32, position in the body-grouped member list: fixes the order of every body sum, so they are deterministic) */
+PST_API pst_status pst_bodies_create(pst_ctx* ctx, uint32_t n_bodies);
+/* after uploading body, x y z, u v w, m, inertia: mass, centre of mass, mass-weighted velocity, offsets and inertia
+ * tensor of every body; orientation = identity, omega = 0; members take the rigid motion */
+PST_API pst_status pst_bodies_setup(pst_ctx* ctx);
+/* checkpoint restore: body, bpos, bx0 by0 bz0 were uploaded as saved; rebuilds the member-list ranges only (the saved
+ * member order, and with it the bit pattern of every body sum, is kept); the records follow through pst_bodies_state */
+PST_API pst_status pst_bodies_restore(pst_ctx* ctx);
+/* read (write = 0) / write (write = 1) a per-body quantity, host data always double, body-major:
+ * "mass" [nb] | "cm" "vel" "omega" "force" "torque" [nb][3] | "rot" [nb][9] row-major | "inertia0" [nb][6] xx yy zz xy xz yz.
+ * Writable: everything but force and torque (members are moved accordingly; mass and inertia0 are normally left to
+ * pst_bodies_setup and only written when a checkpoint is restored). */
+PST_API pst_status pst_bodies_state(pst_ctx* ctx, const char* name, double* host, size_t n, int write);
 
 /* ---- multi-GPU: slab decomposition along x, ghost layers by NCCL send/recv ----------------- */
 #define PST_COMM_ID_BYTES 128

@@ -462,7 +462,8 @@ int dem_forces(const DemParams& P, const Grid* g /* null => all pairs */, int64_
 // Tags: 0 fluid, 1 boundary (static), 2 solid (mobile rigid sphere, one particle per body).
 //   * SPH mass of j: m_j for fluid and boundary, m_j * rho0 / rho_solid (the displaced fluid mass) for solids;
 //   * an SPH pair (i, j) is active iff tag_i == 0 or tag_j == 0 (same neighbour rule and body as WCSPH);
-//   * a DEM pair (i, j) is active iff tag_i == 2 and tag_j != 0 (same contact rule, body and history as DEM);
+//   * a DEM pair (i, j) is active iff tag_i == 2 and tag_j != 0 (same contact rule, body and history as DEM) and,
+//     with rigid bodies, i and j are not members of the same body;
 //   * outputs: au av aw arho (SPH sums, g added to a) for every particle, fx..tz + history for solids only.
 // `ms` is the SPH-mass array (computed by the caller from m, tag, rho0 / rho_solid).
 // ----------------------------------------------------------------------------
@@ -470,6 +471,7 @@ template <class R>
 int coupled_forces(const WcsphParams& PW, const DemParams& PD, const Grid* g /* null => all pairs */, int64_t n,
                    const R* x, const R* y, const R* z, const R* u, const R* v, const R* w, const R* rho, const R* ms,
                    const R* h, const R* wx, const R* wy, const R* wz, const R* rad, const R* m, const int32_t* tag,
+                   const int32_t* rbody /* null, or rigid-body index per particle (-1 = none) */,
                    const uint32_t* id, const int32_t* hn_in, const uint32_t* hid_in, const R* hx_in, const R* hy_in,
                    const R* hz_in, R* p, R* au, R* av, R* aw, R* arho, int32_t* hn_out, uint32_t* hid_out, R* hx_out,
                    R* hy_out, R* hz_out, R* fx, R* fy, R* fz, R* tx, R* ty, R* tz) {
@@ -487,7 +489,7 @@ int coupled_forces(const WcsphParams& PW, const DemParams& PD, const Grid* g /* 
             if (j == i) return;
             if (tag[i] == 0 || tag[j] == 0)
                 wcsph_pair<R>(PW, i, j, x, y, z, u, v, w, rho, ms, h, p, a);
-            if (tag[i] == 2 && tag[j] != 0)
+            if (tag[i] == 2 && tag[j] != 0 && !(rbody && rbody[i] >= 0 && rbody[j] == rbody[i]))
                 dem_pair<R>(PD, n, i, j, x, y, z, u, v, w, wx, wy, wz, rad, m, id, hn_in, hid_in, hx_in, hy_in, hz_in,
                             n, cnt, hid_out, hx_out, hy_out, hz_out, i, d, ov);
         };
@@ -570,12 +572,13 @@ ORC_API void orc_set_num_threads(int n) {
     }                                                                                                         \
     ORC_API int orc_coupled_forces_##SFX(const WcsphParams* PW, const DemParams* PD, const Grid* g, int64_t n, \
                                          const R* const* in /* x y z u v w rho ms h wx wy wz rad m */,         \
-                                         const int32_t* tag, const uint32_t* id, const int32_t* hn_in,         \
+                                         const int32_t* tag, const int32_t* body, const uint32_t* id,          \
+                                         const int32_t* hn_in,                                                 \
                                          const uint32_t* hid_in, const R* hx_in, const R* hy_in,               \
                                          const R* hz_in, R* const* out /* p au av aw arho fx fy fz tx ty tz */, \
                                          int32_t* hn_out, uint32_t* hid_out, R* hx_out, R* hy_out, R* hz_out) { \
         return coupled_forces<R>(*PW, *PD, g, n, in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], in[8], \
-                                 in[9], in[10], in[11], in[12], in[13], tag, id, hn_in, hid_in, hx_in, hy_in,  \
+                                 in[9], in[10], in[11], in[12], in[13], tag, body, id, hn_in, hid_in, hx_in, hy_in,  \
                                  hz_in, out[0], out[1], out[2], out[3], out[4], hn_out, hid_out, hx_out,       \
                                  hy_out, hz_out, out[5], out[6], out[7], out[8], out[9], out[10]);             \
     }

@@ -211,8 +211,9 @@ def coupled(P: dict, K: int, a: dict, hist: dict | None = None, ids: np.ndarray 
     out_ptrs = (C.c_void_p * len(names_out))(*[out[k].ctypes.data for k in names_out])
     wp, dp = wcsph_params(3, P), dem_params(P, K)
     tag = np.ascontiguousarray(a["tag"], np.int32)
+    body = np.ascontiguousarray(a["body"], np.int32) if "body" in a else None   # rigid bodies: same-body contacts are skipped
     ov = getattr(lib(), f"orc_coupled_forces_{_sfx(x)}")(
-        C.byref(wp), C.byref(dp), C.byref(grid) if grid is not None else None, C.c_int64(n), in_ptrs, _p(tag), _p(ids),
+        C.byref(wp), C.byref(dp), C.byref(grid) if grid is not None else None, C.c_int64(n), in_ptrs, _p(tag), _p(body), _p(ids),
         _p(np.ascontiguousarray(hist["hist_n"])), _p(np.ascontiguousarray(hist["hist_id"])),
         _p(np.ascontiguousarray(hist["hist_x"])), _p(np.ascontiguousarray(hist["hist_y"])),
         _p(np.ascontiguousarray(hist["hist_z"])), out_ptrs,
@@ -242,6 +243,106 @@ def coupled_integrate(a: dict, r: dict, P: dict, dt: float) -> dict:
     for om, tq in (("wx", "tx"), ("wy", "ty"), ("wz", "tz")):
         new[om] = np.where(so, a[om] + r[tq] * ii * dt, a[om])
     return new
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Multi-particle rigid bodies.  numpy restatement, always float64; no reference code
+# exists for this physics -- this is the repo's own written contract, like Appendix A.
+# A body record: dict M [nb], X V W F T [nb,3], R [nb,3,3], I0 [nb,3,3].
+# ---------------------------------------------------------------------------------------------------------------
+def rigid_setup(a: dict, nb: int):
+    """Mass, centre of mass, mass-weighted velocity, body-frame offsets r0 = x - X (rounded to the particle dtype) and
+    body-frame inertia I0 = sum m (|r0|^2 1 - r0 r0^T) + inertia_i 1 of every body; R = identity, omega = 0.
+    Returns (bodies, r0 [n,3]); r0 rows of non-members are zero."""
+    body = np.asarray(a["body"])
+    mem = body >= 0
+    bi = body[mem]
+    f8 = lambda k: np.asarray(a[k], np.float64)[mem]
+    m = f8("m")
+    pos = np.stack([f8("x"), f8("y"), f8("z")], axis=1)
+    vel = np.stack([f8("u"), f8("v"), f8("w")], axis=1)
+    M = np.bincount(bi, m, nb)
+    safe = np.where(M > 0, M, 1.0)
+    X = np.stack([np.bincount(bi, m * pos[:, k], nb) for k in range(3)], axis=1) / safe[:, None]
+    V = np.stack([np.bincount(bi, m * vel[:, k], nb) for k in range(3)], axis=1) / safe[:, None]
+    r0m = (pos - X[bi]).astype(np.asarray(a["x"]).dtype).astype(np.float64)
+    r2 = np.sum(r0m * r0m, axis=1)
+    I0 = np.zeros((nb, 3, 3))
+    ins = f8("inertia")
+    for p in range(3):
+        for q in range(3):
+            term = -m * r0m[:, p] * r0m[:, q]
+            if p == q:
+                term = term + m * r2 + ins
+            I0[:, p, q] = np.bincount(bi, term, nb)
+    r0 = np.zeros((len(body), 3))
+    r0[mem] = r0m
+    bodies = {"M": M, "X": X, "V": V, "W": np.zeros((nb, 3)), "R": np.tile(np.eye(3), (nb, 1, 1)), "I0": I0,
+              "F": np.zeros((nb, 3)), "T": np.zeros((nb, 3))}
+    return bodies, r0
+
+
+def rigid_members(bodies: dict, body: np.ndarray, r0: np.ndarray):
+    """Member particles from the body state: x = X + R r0, v = V + W x (x - X), spin = W.  Returns (mask, x, v, w)."""
+    mem = body >= 0
+    bi = body[mem]
+    r = np.einsum("npq,nq->np", bodies["R"][bi], r0[mem])
+    x = bodies["X"][bi] + r
+    v = bodies["V"][bi] + np.cross(bodies["W"][bi], r)
+    return mem, x, v, bodies["W"][bi]
+
+
+def rigid_reduce(a: dict, r: dict, P: dict, bodies: dict) -> dict:
+    """F_b = sum Ft_i, T_b = sum (x_i - X_b) x Ft_i + t_i over the members, Ft_i = m_i ((f_i / m_i + ratio (a_i - g)) + g)
+    (the single-sphere expression of coupled_integrate times m_i).  Constants are rounded to the particle dtype first,
+    as the device does."""
+    T = np.asarray(a["x"]).dtype.type
+    body = np.asarray(a["body"])
+    nb = len(bodies["M"])
+    mem = body >= 0
+    bi = body[mem]
+    f8 = lambda d, k: np.asarray(d[k], np.float64)[mem]
+    ratio = float(T(P["rho0"]) / T(P["rho_solid"]))
+    g = [float(T(P.get("gx", 0.0))), float(T(P.get("gy", 0.0))), float(T(P.get("gz", 0.0)))]
+    m = f8(a, "m")
+    Ft = np.stack([m * ((f8(r, fk) / m + ratio * (f8(r, ak) - gk)) + gk)
+                   for fk, ak, gk in (("fx", "au", g[0]), ("fy", "av", g[1]), ("fz", "aw", g[2]))], axis=1)
+    pos = np.stack([f8(a, "x"), f8(a, "y"), f8(a, "z")], axis=1)
+    tq = np.cross(pos - bodies["X"][bi], Ft) + np.stack([f8(r, "tx"), f8(r, "ty"), f8(r, "tz")], axis=1)
+    out = dict(bodies)
+    out["F"] = np.stack([np.bincount(bi, Ft[:, k], nb) for k in range(3)], axis=1)
+    out["T"] = np.stack([np.bincount(bi, tq[:, k], nb) for k in range(3)], axis=1)
+    return out
+
+
+def rigid_integrate(bodies: dict, dt: float) -> dict:
+    """Semi-implicit Euler stage of the bodies: V += F/M dt; X += V dt; W += I^-1 (T - W x (I W)) dt with
+    I = R I0 R^T; R <- exp([W dt]x) R (Rodrigues).  Bodies without mass are left alone."""
+    b = {k: np.array(v, copy=True) for k, v in bodies.items()}
+    ok = b["M"] > 0
+    M = np.where(ok, b["M"], 1.0)
+    V = b["V"] + b["F"] / M[:, None] * dt
+    X = b["X"] + V * dt
+    I = np.einsum("npq,nqr,nsr->nps", b["R"], b["I0"], b["R"])
+    I = np.where(ok[:, None, None], I, np.eye(3))
+    Iw = np.einsum("npq,nq->np", I, b["W"])
+    rhs = b["T"] - np.cross(b["W"], Iw)
+    W = b["W"] + np.linalg.solve(I, rhs[:, :, None])[:, :, 0] * dt
+    ang = W * dt
+    th = np.linalg.norm(ang, axis=1)
+    small = th < 1e-12
+    ths = np.where(small, 1.0, th)
+    s = np.where(small, 1.0, np.sin(ths) / ths)
+    c = np.where(small, 0.5, (1.0 - np.cos(ths)) / (ths * ths))
+    K = np.zeros((len(th), 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -ang[:, 2], ang[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = ang[:, 2], -ang[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -ang[:, 1], ang[:, 0]
+    E = np.eye(3) + s[:, None, None] * K + c[:, None, None] * (K @ K)
+    R = E @ b["R"]
+    for k, v in (("V", V), ("X", X), ("W", W), ("R", R)):
+        b[k] = np.where(ok.reshape((-1,) + (1,) * (v.ndim - 1)), v, bodies[k])
+    return b
 
 
 def history_as_dict(hist: dict, ids: np.ndarray | None = None) -> dict:

@@ -34,7 +34,7 @@ SYMBOLS = [
     "pst_get_param", "pst_set_count", "pst_get_count", "pst_array_create", "pst_array", "pst_upload",
     "pst_download", "pst_upload_async", "pst_download_async", "pst_wait_transfers", "pst_host_alloc", "pst_host_free", "pst_build_neighbours", "pst_apply", "pst_dump_pairs",
     "pst_step", "pst_integrate", "pst_get_stat", "pst_set_option", "pst_comm_unique_id", "pst_comm_init",
-    "pst_halo_exchange",
+    "pst_halo_exchange", "pst_bodies_create", "pst_bodies_setup", "pst_bodies_restore", "pst_bodies_state",
 ]
 
 _lib = None
@@ -80,6 +80,10 @@ def load() -> C.CDLL:
     lib.pst_comm_unique_id.argtypes = [vp]; lib.pst_comm_unique_id.restype = st
     lib.pst_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]; lib.pst_comm_init.restype = st
     lib.pst_halo_exchange.argtypes = [vp]; lib.pst_halo_exchange.restype = st
+    lib.pst_bodies_create.argtypes = [vp, C.c_uint32]; lib.pst_bodies_create.restype = st
+    lib.pst_bodies_setup.argtypes = [vp]; lib.pst_bodies_setup.restype = st
+    lib.pst_bodies_restore.argtypes = [vp]; lib.pst_bodies_restore.restype = st
+    lib.pst_bodies_state.argtypes = [vp, cp, vp, C.c_size_t, C.c_int]; lib.pst_bodies_state.restype = st
     _lib = lib
     return lib
 

@@ -142,11 +142,15 @@ class Context:
         self.set_count(block.n)
         known = {k: v for k, v in block.params.items()}
         self.set_params(**known)
+        if "body" in block.arrays and (arrays is None or "body" in arrays) and not self.has_array("body"):
+            self.bodies_create(block.meta["n_bodies"])
         for k, v in block.arrays.items():
             if arrays is not None and k not in arrays:
                 continue
             if self.has_array(k):
                 self.upload(k, v)
+        if "body" in block.arrays and (arrays is None or "body" in arrays):
+            self.bodies_setup()
 
     # -- the hot path -----------------------------------------------------------------------
     def refresh_count(self) -> int:
@@ -183,6 +187,33 @@ class Context:
         v = C.c_double()
         self._ck(self._lib.pst_get_stat(self._h, name.encode(), C.byref(v)))
         return v.value
+
+    # -- multi-particle rigid bodies (coupled contexts) ---------------------------------------
+    _BODY_WIDTH = {"mass": 1, "cm": 3, "vel": 3, "omega": 3, "rot": 9, "inertia0": 6, "force": 3, "torque": 3}
+
+    def bodies_create(self, n_bodies: int):
+        self._ck(self._lib.pst_bodies_create(self._h, int(n_bodies)))
+        self.n_bodies = int(n_bodies)
+
+    def bodies_setup(self):
+        """After `body`, positions, velocities, m and inertia are uploaded: mass, centre of mass, velocity, offsets and
+        inertia tensor of every body; members take the rigid motion."""
+        self._ck(self._lib.pst_bodies_setup(self._h))
+
+    def bodies_restore(self):
+        """Checkpoint restore: body, bpos, bx0 by0 bz0 uploaded as saved; the records follow through body_set."""
+        self._ck(self._lib.pst_bodies_restore(self._h))
+
+    def body_get(self, name: str) -> np.ndarray:
+        w = self._BODY_WIDTH[name]
+        out = np.empty((self.n_bodies, w) if w > 1 else self.n_bodies, np.float64)
+        self._ck(self._lib.pst_bodies_state(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size, 0))
+        return out
+
+    def body_set(self, name: str, value: np.ndarray):
+        a = np.ascontiguousarray(value, np.float64)
+        assert a.size == self.n_bodies * self._BODY_WIDTH[name]
+        self._ck(self._lib.pst_bodies_state(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size, 1))
 
     # -- multi-GPU --------------------------------------------------------------------------
     @staticmethod

@@ -176,7 +176,7 @@ void pst_destroy(pst_ctx* ctx) {
     pst_comm_destroy(ctx);
     for (auto& a : ctx->arrays) { cudaFree(a.buf[0]); if (a.buf[1]) cudaFree(a.buf[1]); }
     cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
-    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->stage); cudaFree(ctx->d_flags);
+    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
     cudaFree(ctx->d_counters);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -331,6 +331,7 @@ pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;
     ctx->hist_lag = false;
+    ctx->bodies_ready = false;       // a new particle set: pst_bodies_setup again
     PST_TRY(pst_iota_ids(ctx));
     if (PstArray* hn = pst_find(ctx, "hist_n")) {
         const size_t stride = ctx->capacity + 2 * ctx->ghost_cap;
@@ -447,7 +448,7 @@ pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
         if (!eq_names[k]) return PST_EINVAL;
         eqs.insert(eq_names[k]);
     }
-    static const std::set<std::string> known = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact"};
+    static const std::set<std::string> known = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact", "body_reduce"};
     for (auto& e : eqs)
         if (!known.count(e)) return pst_fail(ctx, PST_EINVAL, "no hand-written kernel for equation '%s'", e.c_str());
     // fuse(): group the set into the fused kernels that exist.  Bodies that share an i,j loop
@@ -472,6 +473,10 @@ pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
         if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pair equations");
         PST_TRY(pst_dem_forces(ctx));
     }
+    if (eqs.count("body_reduce")) {   // per-particle results of the force loop -> force and torque of every rigid body (runs last)
+        if (!ctx->d_bodies) return pst_fail(ctx, PST_ESTATE, "body_reduce: the context has no rigid bodies (pst_bodies_create)");
+        PST_TRY(pst_rb_reduce(ctx));
+    }
     return PST_OK;
 }
 
@@ -485,8 +490,13 @@ pst_status pst_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size
 pst_status pst_integrate(pst_ctx* ctx, double dt) {
     if (!ctx) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    if (ctx->coupled) PST_TRY(pst_coupled_integrate(ctx, dt));
-    else if (ctx->cfg.physics & PST_PHYS_WCSPH) PST_TRY(pst_wcsph_integrate(ctx, dt));
+    if (ctx->coupled) {
+        // rigid bodies: reduce the current per-particle forces, advance free particles (members are moved too, as if
+        // free, and then overwritten), advance the bodies and scatter the rigid motion onto their members
+        if (ctx->bodies_ready) PST_TRY(pst_rb_reduce(ctx));
+        PST_TRY(pst_coupled_integrate(ctx, dt));
+        if (ctx->bodies_ready) PST_TRY(pst_rb_integrate(ctx, dt));
+    } else if (ctx->cfg.physics & PST_PHYS_WCSPH) PST_TRY(pst_wcsph_integrate(ctx, dt));
     else if (ctx->cfg.physics & PST_PHYS_DEM) PST_TRY(pst_dem_integrate(ctx, dt));
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;

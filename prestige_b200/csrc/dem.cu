@@ -27,6 +27,7 @@ struct DemArgs {
     const R *x, *y, *z, *u, *v, *w, *wx, *wy, *wz, *rad, *m;
     const uint32_t* id;
     const int32_t* tag;      // coupled SPH-DEM contexts only (else nullptr): i must be a solid (tag 2), j must not be fluid (tag 0)
+    const int32_t* body;     // rigid bodies (rigid.cu; else nullptr): members of the same body (index >= 0) are not contact partners
     const int32_t* hn_in; const uint32_t* hid_in; const R *hx_in, *hy_in, *hz_in;
     const uint32_t* hperm;   // deferred history remap: old row of particle s is hperm[s] (nullptr: rows already in place)
     int32_t* hn_out; uint32_t* hid_out; R *hx_out, *hy_out, *hz_out;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
             const R rs = add_rn(ri, A.rad[j]);
             if (!(r2 < mul_rn(rs, rs)) || !(r2 > (R)0) || j == s) continue;
             if (A.tag && A.tag[j] == 0) continue;
+            if (A.body && A.body[s] >= 0 && A.body[j] == A.body[s]) continue;
             dem_contact<R>(C, A, s, j, xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
         }
     });
@@ -201,7 +203,8 @@ __global__ void __launch_bounds__(256) k_nf_fill(int lo, int hi, const int32_t* 
 // at a time with their 16 loads in flight together and only records the hits, (3) the heavy contact body then
 // runs on the recorded hits.  The kernel is a latency-bound gather, so the win is memory-level parallelism.
 // NF (coupled contexts): threads and candidates come from the compacted non-fluid list (see above).
-template <class R, bool NF>
+// BODIES (coupled contexts with rigid bodies): members of the same body are skipped as contact partners.
+template <class R, bool NF, bool BODIES = false>
 __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemConst<R> C, DemArgs<R> A, NfArgs F) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int own = s;                                        // NF: this thread's compacted index
@@ -269,8 +272,12 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
     const int nold = A.hn_in[hrow];
     R fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     int cnt = 0;
-    for (int h = 0; h < min(nh, kHits); ++h)
-        dem_contact<R>(C, A, s, NF ? F.idx[hits[h]] : hits[h], xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
+    const int bi = BODIES ? A.body[s] : -1;
+    for (int h = 0; h < min(nh, kHits); ++h) {
+        const int j = NF ? F.idx[hits[h]] : hits[h];
+        if (BODIES && bi >= 0 && A.body[j] == bi) continue;          // same rigid body: no internal contacts
+        dem_contact<R>(C, A, s, j, xi, yi, zi, ui, vi, wi, ri, mi, owx, owy, owz, nold, hrow, fx, fy, fz, tx, ty, tz, cnt);
+    }
     if (nh > kHits) cnt = nh;          // more contacts than can ever be stored: reported as overflow below
     dem_finish<R>(C, A, s, cnt, fx, fy, fz, tx, ty, tz);
 }
@@ -313,6 +320,7 @@ pst_status launch_dem(pst_ctx* ctx) {
     A.wx = pst_ptr<R>(ctx, "wx"); A.wy = pst_ptr<R>(ctx, "wy"); A.wz = pst_ptr<R>(ctx, "wz");
     A.rad = pst_ptr<R>(ctx, "rad"); A.m = pst_ptr<R>(ctx, "m"); A.id = pst_ptr<uint32_t>(ctx, "id");
     A.tag = ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr;
+    A.body = ctx->bodies_ready ? pst_ptr<int32_t>(ctx, "body") : nullptr;
     const int c = hn->cur, d = 1 - hn->cur;
     A.hn_in = pst_ptr<int32_t>(ctx, hn, 0, c); A.hid_in = pst_ptr<uint32_t>(ctx, hid, 0, c);
     A.hx_in = pst_ptr<R>(ctx, hx, 0, c); A.hy_in = pst_ptr<R>(ctx, hy, 0, c); A.hz_in = pst_ptr<R>(ctx, hz, 0, c);
@@ -353,7 +361,10 @@ pst_status launch_dem(pst_ctx* ctx) {
         PST_TRY(pst_scan_exclusive(ctx, ctx->nf_pos, m));
         PST_LAUNCH(ctx, k_nf_fill<R>, blocks_for(m, 256), 256, 0, lo, hi, A.tag, ctx->nf_pos, A.x, A.y, A.z, A.rad, ctx->nf_idx, (R*)ctx->nf_rec, total_copy);
         F = NfArgs{ctx->nf_pos, ctx->nf_idx, ctx->nf_rec, lo, hi};
-        PST_LAUNCH(ctx, (k_dem_forces<R, true>), blocks_for(m, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
+        if (A.body) PST_LAUNCH(ctx, (k_dem_forces<R, true, true>), blocks_for(m, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
+        else PST_LAUNCH(ctx, (k_dem_forces<R, true>), blocks_for(m, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
+    } else if (A.body) {
+        PST_LAUNCH(ctx, (k_dem_forces<R, false, true>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
     } else {
         PST_LAUNCH(ctx, (k_dem_forces<R, false>), blocks_for(ctx->n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), C, A, F);
     }

@@ -253,6 +253,7 @@ extern "C" pst_status pst_comm_init(pst_ctx* ctx, const void* id_bytes, int rank
     if (ctx->comm) return pst_fail(ctx, PST_ESTATE, "communicator already attached");
     if (ctx->grid.morton) return pst_fail(ctx, PST_EINVAL, "slab decomposition needs linear keys (x slowest)");
     if (ctx->ghost_cap == 0) return pst_fail(ctx, PST_EINVAL, "pst_config.ghost_capacity is 0");
+    if (ctx->d_bodies) return pst_fail(ctx, PST_ESTATE, "rigid bodies are not supported with a communicator attached");
     NcclApi* api = nccl_api();
     if (!api->lib) return pst_fail(ctx, PST_ENCCL, "%s", api->err.c_str());
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));

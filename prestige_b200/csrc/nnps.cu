@@ -271,7 +271,7 @@ template <class R, int DIM, bool MORTON>
 __global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, int mode, R kfac, const int32_t* __restrict__ cell_start,
                                                          const R* __restrict__ x, const R* __restrict__ y, const R* __restrict__ z,
                                                          const R* __restrict__ sz, const uint32_t* __restrict__ id,
-                                                         const int32_t* __restrict__ tag,
+                                                         const int32_t* __restrict__ tag, const int32_t* __restrict__ body,
                                                          uint32_t* __restrict__ oi, uint32_t* __restrict__ oj,
                                                          unsigned long long cap, unsigned long long* __restrict__ counter) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,10 +283,12 @@ __global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, in
     const uint32_t idi = id[s];
     const int ti = tag ? tag[s] : 0;
     if (tag && mode == 1 && ti != 2) return;
+    const int bi = (body && mode == 1) ? body[s] : -1;       // rigid bodies: members of one body are not contact partners
     for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
         for (int j = b; j < e; ++j) {
             if (j == s) continue;
             if (tag && (mode == 0 ? (ti != 0 && tag[j] != 0) : tag[j] == 0)) continue;
+            if (bi >= 0 && body[j] == bi) continue;
             const R r2 = dist2<DIM, R>(xi - x[j], yi - y[j], DIM == 3 ? zi - z[j] : (R)0);
             const R rc = mode == 0 ? mul_rn(kfac, si) : add_rn(si, sz[j]);
             if (r2 < mul_rn(rc, rc)) {
@@ -321,7 +323,7 @@ pst_status launch_dump(pst_ctx* ctx, int mode, const void* sz, uint32_t* oi, uin
     PST_LAUNCH(ctx, (k_dump_pairs<R, DIM, MORTON>), blocks_for(n), kThreads, 0, make_grid_dev<R>(ctx->grid), n, mode,
                (R)pst_param(ctx, "kfac", 2.0), ctx->cell_start, pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"),
                DIM == 3 ? pst_ptr<R>(ctx, "z") : nullptr, (const R*)sz, pst_ptr<uint32_t>(ctx, "id"),
-               ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr, oi, oj,
+               ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr, ctx->bodies_ready ? pst_ptr<int32_t>(ctx, "body") : nullptr, oi, oj,
                (unsigned long long)cap, ctx->d_counters);
     return PST_OK;
 }
@@ -456,6 +458,16 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     ctx->ordered = true;
     ctx->nbrs_valid = true;
     ctx->eos_valid = false;
+    return PST_OK;
+}
+
+// stable sort of n (key, value) u32 pairs: keys_in/vals_in -> keys_out/vals_out (library sort; used by one-time set-up
+// work such as the rigid-body member lists, never on the per-step path, whose sort is the counting sort above)
+pst_status pst_sort_pairs_u32(pst_ctx* ctx, int n) {
+    if (n <= 0) return PST_OK;
+    size_t tmp = ctx->sort_tmp_bytes;
+    PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp, tmp, ctx->keys_in, ctx->keys_out, ctx->vals_in, ctx->vals_out, n, 0, 32, ctx->stream));
+    ctx->launches += 6;
     return PST_OK;
 }
 

@@ -83,6 +83,13 @@ struct pst_ctx {
     cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)
     bool stats_pending = false;
     PstComm* comm = nullptr;
+    // multi-particle rigid bodies (rigid.cu): per-body records, field-major (rigid_core.h RbField), always double
+    uint32_t n_bodies = 0;
+    double* d_bodies = nullptr;
+    int32_t* d_body_start = nullptr; // n_bodies + 1: member-list range of every body (members grouped by body, fixed order)
+    double* d_body_vals = nullptr;   // per-member scratch of the body sums, field-major with stride body_members
+    size_t body_members = 0;         // total member particles
+    bool bodies_ready = false;       // pst_bodies_setup has run for the current particle set
     mutable std::string err;
 };
 
@@ -127,6 +134,7 @@ int pst_option(pst_ctx* ctx, const char* name, int dflt = 0);
 pst_status pst_nnps_build(pst_ctx* ctx);                                 // nnps.cu
 pst_status pst_nnps_alloc(pst_ctx* ctx);
 pst_status pst_scan_exclusive(pst_ctx* ctx, int32_t* a, int m);        // in place, m entries (nnps.cu)
+pst_status pst_sort_pairs_u32(pst_ctx* ctx, int n);                       // keys_in/vals_in -> keys_out/vals_out, stable (nnps.cu)
 pst_status pst_resolve_history(pst_ctx* ctx);   // run the deferred k_remap_history, if any
 pst_status pst_nnps_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size_t cap, size_t* n_pairs);
 pst_status pst_reorder_upload(pst_ctx* ctx, PstArray* a, int row, size_t n);   // stage -> array (by id)
@@ -139,6 +147,8 @@ pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu
 pst_status pst_dem_integrate(pst_ctx* ctx, double dt);
 pst_status pst_coupled_integrate(pst_ctx* ctx, double dt);                // wcsph.cu
+pst_status pst_rb_reduce(pst_ctx* ctx);                                   // rigid.cu: per-particle forces -> body force / torque
+pst_status pst_rb_integrate(pst_ctx* ctx, double dt);                     // body stage + member scatter
 pst_status pst_comm_destroy(pst_ctx* ctx);                                // halo.cu
 void pst_comm_neighbours(pst_ctx* ctx, int* has_left, int* has_right);
 pst_status pst_ghost_counts(pst_ctx* ctx, int64_t* nl, int64_t* nr);

@@ -144,3 +144,7 @@ momentum = declare("momentum", ["x", "y", "z", "u", "v", "w", "m", "h", "rho", "
 dem_contact = declare("dem_contact", ["x", "y", "z", "u", "v", "w", "wx", "wy", "wz", "rad", "m", "hist_id", "hist_x", "hist_y", "hist_z", "hist_n"],
                       ["fx", "fy", "fz", "tx", "ty", "tz", "hist_id", "hist_x", "hist_y", "hist_z", "hist_n"],
                       "{ (F[i], T[i], xi[i][j]) += spring_dashpot(x_ij, v_ij, w, rad, xi[i][j]) ; }")
+# per-particle (no j): sums the force loop's results over the members of each rigid body
+body_reduce = declare("body_reduce", ["x", "y", "z", "m", "body", "fx", "fy", "fz", "tx", "ty", "tz", "au", "av", "aw"],
+                      ["body_force", "body_torque"],
+                      "{ body_force[body[i]] += f_total(i) ; body_torque[body[i]] += cross(x[i] - cm[body[i]], f_total(i)) + t[i] ; }")

@@ -9,11 +9,13 @@ import numpy as np
 _STATE_WCSPH = ["x", "y", "z", "u", "v", "w", "rho", "m", "h", "tag"]
 _STATE_DEM = ["x", "y", "z", "u", "v", "w", "wx", "wy", "wz", "rad", "m", "inertia", "tag"]
 _HISTORY = ["hist_n", "hist_id", "hist_x", "hist_y", "hist_z"]
+_RIGID = ["body", "bpos", "bx0", "by0", "bz0"]                                   # particle side of the rigid bodies
+_BODY_STATE = ["mass", "inertia0", "cm", "vel", "omega", "rot"]          # per-body records, restored in this order
 
 
 def state_names(ctx) -> list:
     names = []
-    for k in _STATE_WCSPH + _STATE_DEM + _HISTORY:
+    for k in _STATE_WCSPH + _STATE_DEM + _HISTORY + _RIGID:
         if k not in names and ctx.has_array(k):
             names.append(k)
     return names
@@ -28,6 +30,9 @@ def save_checkpoint(ctx, path: str, extra: dict | None = None) -> None:
     data = {k: ctx.download(k) for k in state_names(ctx)}
     data["__n"] = np.array([ctx.n], np.int64)
     data["__order"] = ctx.download("id")
+    if ctx.has_array("body"):
+        for k in _BODY_STATE:
+            data["__body_" + k] = ctx.body_get(k)
     for k, v in (extra or {}).items():
         data["__extra_" + k] = np.asarray(v)
     np.savez(path, **data)
@@ -39,6 +44,9 @@ def load_checkpoint(ctx, path: str) -> dict:
     n = int(z["__n"][0])
     order = z["__order"].astype(np.uint32)
     ctx.set_count(n)                                  # identity order: uploads land slot by slot
+    rigid = "__body_mass" in z.files
+    if rigid and not ctx.has_array("body"):
+        ctx.bodies_create(len(z["__body_mass"]))
     for k in z.files:
         if k.startswith("__"):
             continue
@@ -46,6 +54,13 @@ def load_checkpoint(ctx, path: str) -> dict:
             raise KeyError(f"checkpoint array '{k}' does not exist in this context")
         ctx.upload(k, np.ascontiguousarray(z[k][..., order]))     # id order -> saved device order
     ctx.upload("id", order)                           # declare the ids; host arrays are id-ordered again from here on
+    if rigid:
+        # member-list ranges from `body`; the saved positions `bpos` (the order of every body sum) are kept.
+        ctx.bodies_restore()
+        # every write scatters x = X + R r0, v = V + w x r onto the members; after the last one the records are
+        # complete and the scatter repeats the arithmetic that produced the saved particle state: bit-identical resume
+        for k in _BODY_STATE:
+            ctx.body_set(k, z["__body_" + k])
     return {k[len("__extra_"):]: z[k] for k in z.files if k.startswith("__extra_")}
 
 

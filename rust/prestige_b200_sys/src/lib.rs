@@ -78,4 +78,8 @@ unsafe extern "C" {
     pub fn pst_comm_unique_id(id_bytes: *mut c_void) -> pst_status;
     pub fn pst_comm_init(ctx: *mut pst_ctx, id_bytes: *const c_void, rank: c_int, n_ranks: c_int) -> pst_status;
     pub fn pst_halo_exchange(ctx: *mut pst_ctx) -> pst_status;
+    pub fn pst_bodies_create(ctx: *mut pst_ctx, n_bodies: u32) -> pst_status;
+    pub fn pst_bodies_setup(ctx: *mut pst_ctx) -> pst_status;
+    pub fn pst_bodies_restore(ctx: *mut pst_ctx) -> pst_status;
+    pub fn pst_bodies_state(ctx: *mut pst_ctx, name: *const c_char, host: *mut c_double, n: usize, write: c_int) -> pst_status;
 }
