@@ -38,6 +38,25 @@ int pst_option(pst_ctx* ctx, const char* name, int dflt) {
 
 static size_t dtype_size(int dt) { return (dt == PST_F64) ? 8 : 4; }
 
+// "m" arrives from the host only (pst_upload / pst_upload_async): remember whether all masses are equal, so the fused
+// pair kernel can use the value instead of gathering m[j] for every pair (one of its nine 8-byte gathers).
+static void note_mass_upload(pst_ctx* ctx, const PstArray* a, const void* host, size_t n) {
+    if (a->name != "m") return;
+    ctx->m_uniform = false;
+    if (n == 0) return;
+    bool same = true;
+    if (a->dtype == PST_F64) {
+        const double* h = (const double*)host;
+        for (size_t k = 1; k < n && same; ++k) same = h[k] == h[0];
+        ctx->m_value = h[0];
+    } else {
+        const float* h = (const float*)host;
+        for (size_t k = 1; k < n && same; ++k) same = h[k] == h[0];
+        ctx->m_value = (double)h[0];
+    }
+    ctx->m_uniform = same;
+}
+
 static pst_status array_create(pst_ctx* ctx, const char* name, int dtype, uint32_t flags, int rows) {
     if (!name || !*name) return pst_fail(ctx, PST_EINVAL, "array name is empty");
     if (pst_find(ctx, name)) return pst_fail(ctx, PST_EINVAL, "array '%s' already exists", name);
@@ -263,6 +282,7 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
     if (!ctx->ordered || ctx->comm || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / distributed mode / history rows: plain path
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    note_mass_upload(ctx, a, host, n);
     int k = 0;
     PST_TRY(ring_acquire(ctx, ctx->h2d_stream, true, &k));
     PST_CUDA(ctx, cudaMemcpyAsync(ctx->ring[k], host, n * a->esize, cudaMemcpyHostToDevice, ctx->h2d_stream));
@@ -332,6 +352,7 @@ pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
     ctx->eos_valid = false;
     ctx->hist_lag = false;
     ctx->bodies_ready = false;       // a new particle set: pst_bodies_setup again
+    ctx->m_uniform = false;          // ... and its masses are not known yet
     PST_TRY(pst_iota_ids(ctx));
     if (PstArray* hn = pst_find(ctx, "hist_n")) {
         const size_t stride = ctx->capacity + 2 * ctx->ghost_cap;
@@ -373,6 +394,7 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles (pst_set_count first)", name, n, (unsigned long long)ctx->n);
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    note_mass_upload(ctx, a, host, n);
     if (a->name.rfind("hist_", 0) == 0) PST_TRY(pst_resolve_history(ctx));
     if (a->name == "id") {
         // Restoring a checkpoint in DEVICE order: right after pst_set_count (identity order) the caller may declare

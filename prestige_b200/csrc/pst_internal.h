@@ -78,6 +78,8 @@ struct pst_ctx {
     bool ordered = false;            // device order != id order (a sort has happened)
     bool nbrs_valid = false;
     bool eos_valid = false;
+    bool m_uniform = false;          // every uploaded particle mass is the same value (pair kernels then skip the m[j] gather)
+    double m_value = 0.0;
     bool hist_lag = false;           // contact-history rows still sit at their PRE-sort index (vals_out maps new -> old)
     uint64_t launches = 0;
     cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)

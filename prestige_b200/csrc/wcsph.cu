@@ -131,6 +131,7 @@ __device__ __forceinline__ void pair_body(const WcsphConst<R>& C, const IState<R
 
 template <class R>
 struct ForceArgs {
+    R m_uni;   // UMASS kernels: the mass every particle has
     const R *x, *y, *z, *u, *v, *w, *rho, *m, *h, *por2;
     R *au, *av, *aw, *arho;
     const int32_t* cell_start;
@@ -210,7 +211,8 @@ struct TileDims {
 
 constexpr int kListsJcap = 1536;   // float4 slots staged per tile (24 KB): every KB not requested stays L1 for the phase-2 gathers (2048 -> 1536: -3 %)
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false>
+// UMASS: every particle has the mass A.m_uni (known from the host upload), so m[j] is not gathered.
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UMASS = false>
 __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, TileShape T) {
     using D = TileDims<DIM, TA, TB>;
     constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
                 const bool in0 = r20 < I.rc2 && r20 > (R)0;            // the exact test (the set is defined here)
                 const bool in1 = v1 && r21 < I.rc2 && r21 > (R)0;
                 r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
-                R m0 = in0 ? LD(A.m, j0, 3) : (R)0, m1 = in1 ? LD(A.m, j1, 3) : (R)0;
+                R m0 = in0 ? (UMASS ? A.m_uni : LD(A.m, j0, 3)) : (R)0, m1 = in1 ? (UMASS ? A.m_uni : LD(A.m, j1, 3)) : (R)0;
                 if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
                     m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
                     m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
@@ -683,6 +685,7 @@ ForceArgs<R> make_args(pst_ctx* ctx) {
     A.au = pst_ptr<R>(ctx, "au"); A.av = pst_ptr<R>(ctx, "av"); A.aw = pst_ptr<R>(ctx, "aw"); A.arho = pst_ptr<R>(ctx, "arho");
     A.cell_start = ctx->cell_start;
     A.n = (int)ctx->n;
+    A.m_uni = (R)ctx->m_value;
     return A;
 }
 
@@ -702,11 +705,11 @@ pst_status launch_gather(pst_ctx* ctx, bool cont, bool mom) {
     return PST_OK;
 }
 
-template <class R, int DIM, int TA, int TB, int NT, int VARIANT, bool CONT, bool MOM, bool COUPLED = false>
+template <class R, int DIM, int TA, int TB, int NT, int VARIANT, bool CONT, bool MOM, bool COUPLED = false, bool UMASS = false>
 pst_status launch_tiled_k(pst_ctx* ctx, const TileShape& T, size_t smem) {
     void (*kern)(GridDev<R>, WcsphConst<R>, ForceArgs<R>, TileShape);
     if (VARIANT == 1) kern = k_wcsph_cellwarp<R, DIM, TA, TB, NT, CONT, MOM>;
-    else kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM, COUPLED>;
+    else kern = k_wcsph_tiled<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UMASS>;
     PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const unsigned grid = (unsigned)T.tiles[0] * T.tiles[1] * T.tiles[2];
     PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), make_args<R>(ctx), T);
@@ -747,6 +750,11 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
     if (ctx->coupled) {
         if (DIM == 3 && VARIANT == 2) return launch_tiled_k<R, 3, TA, TB, NT, 2, true, true, true>(ctx, T, smem);
         return pst_fail(ctx, PST_EINVAL, "coupled contexts need dim = 3 and force_kernel 0 or 2");
+    }
+    // all masses equal (seen at upload; single rank, so no foreign ghosts): the fused kernel without the m[j] gather
+    const bool umass = VARIANT == 2 && ctx->m_uniform && !ctx->comm && pst_option(ctx, "uniform_mass", 1) != 0;
+    if constexpr (VARIANT == 2) {
+        if (cont && mom && umass) return launch_tiled_k<R, DIM, TA, TB, NT, 2, true, true, false, true>(ctx, T, smem);
     }
     if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, true>(ctx, T, smem);
     if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, false>(ctx, T, smem);

@@ -119,6 +119,26 @@ def test_wcsph_3d(real, variant):
 
 
 @pytest.mark.parametrize("real", REALS)
+@pytest.mark.parametrize("dim", [3, 2])
+def test_wcsph_nonuniform_and_uniform_mass_paths(real, dim):
+    """The fused kernel skips the m[j] gather when every uploaded mass is equal (the synthetic blocks): that path must
+    equal the general one bit for bit, and a block with unequal masses must still match the oracle (general path)."""
+    b = (synth.wcsph_block_3d(20, 18, 22) if dim == 3 else synth.wcsph_dambreak_2d(dx=0.05)).shuffled()
+    names = ["p", "au", "av", "arho"] + (["aw"] if dim == 3 else [])
+    uni, _ = _wcsph_gpu(b, real)
+    gen, _ = _wcsph_gpu(b, real, opts={"uniform_mass": 0})
+    for k in names:
+        assert np.array_equal(uni[k], gen[k]), f"{k}: uniform-mass path differs from the general path"
+    rng = np.random.default_rng(5)
+    b.arrays["m"] = b.arrays["m"] * rng.uniform(0.8, 1.2, b.n)
+    br = b.astype(real)
+    ref = orc.wcsph(dim, br.params, br.arrays)
+    got, _ = _wcsph_gpu(b, real)
+    for k in names:
+        assert_close(got[k], ref[k], f"non-uniform mass, dim {dim}: {k}")
+
+
+@pytest.mark.parametrize("real", REALS)
 @pytest.mark.parametrize("variant", [0, 1, 2])
 def test_wcsph_2d_dambreak(real, variant):
     b = synth.wcsph_dambreak_2d(dx=0.02).shuffled()
