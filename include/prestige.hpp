@@ -97,6 +97,13 @@ struct dem_contact {
                 "{ (F [i] , T [i] , xi [i] [j]) += spring_dashpot (x_ij , v_ij , w , rad , xi [i] [j]) ; }"};
     }
 };
+// gather over the FLUID neighbours of every dummy (non-fluid) particle: extrapolated pressure + matching density
+struct wall_pressure {
+    static equations::ir::EquationIR ir() {
+        return {"wall_pressure", {"x", "y", "z", "h", "tag", "rho", "p"}, {"p", "rho"},
+                "{ if tag [i] != 0 && tag [j] == 0 { num [i] += (p [j] + rho [j] * dot (g , x_ij)) * w (x_ij , h [i]) ; den [i] += w (x_ij , h [i]) ; } }"};
+    }
+};
 // per-particle (no j): sums the force loop's results over the members of each rigid body
 struct body_reduce {
     static equations::ir::EquationIR ir() {
@@ -125,7 +132,7 @@ inline std::string generate_simple_cpu(const equations::fuse::FusedEquations& ir
 namespace b200 {
 // The launch plan for a fused set: the names pst_apply receives, in body order.
 inline std::vector<std::string> generate_b200(const equations::fuse::FusedEquations& ir) {
-    static const std::set<std::string> kernels = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact", "body_reduce"};
+    static const std::set<std::string> kernels = {"eq1", "tait_eos", "wall_pressure", "continuity", "momentum", "dem_contact", "body_reduce"};
     if (ir.names.empty()) throw std::invalid_argument("FusedEquations.names is empty");
     for (const auto& n : ir.names)
         if (!kernels.count(n)) throw std::invalid_argument("no hand-written kernel for equation '" + n + "'");

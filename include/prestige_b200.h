@@ -132,7 +132,12 @@ PST_API void pst_host_free(void* p);
 /* cell keys -> radix sort -> cell start table -> permute persistent state (+ history remap) */
 PST_API pst_status pst_build_neighbours(pst_ctx* ctx);
 /* fuse(): run the hand-written fused kernel for this equation set, bodies in the given order.
- * Known names: "eq1" | "tait_eos" "continuity" "momentum" | "dem_contact" | "body_reduce"     */
+ * Known names: "eq1" | "tait_eos" "wall_pressure" "continuity" "momentum" | "dem_contact" | "body_reduce"
+ * "wall_pressure" (no reference code): every non-fluid particle (tag != 0) takes the pressure
+ * extrapolated from its fluid neighbours, p_w = sum (p_f + rho_f g . x_wf) W_wf / sum W_wf, and the density the EOS
+ * maps to it (p, por2 and the state array rho are overwritten for those rows); runs after tait_eos and before the
+ * pair kernel.  With the parameter boundary_model = 1 pst_step includes it and the integrator no longer advances the
+ * density of non-fluid particles.  One GPU only (no communicator).                                              */
 PST_API pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq);
 /* parity hook: neighbour set (mode 0: r2 < (kfac h_i)^2) or contact set (mode 1: r2 < (R_i+R_j)^2)
  * as stable ids; order unspecified.  *n_pairs is always the true count; PST_EOVERFLOW if > cap. */

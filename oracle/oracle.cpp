@@ -42,6 +42,8 @@ struct WcsphParams {
     double kfac;      // support radius = kfac * h   (2 for Wendland C2)
     double rho0, c0, gamma, alpha, beta;
     double g[3];
+    int32_t p_given;  // 1: `p` is an INPUT of the pair loops (EOS + wall_pressure already applied by the caller)
+    int32_t pad2;
 };
 
 struct DemParams {
@@ -255,7 +257,7 @@ template <class R>
 void wcsph_allpairs(const WcsphParams& P, int64_t n, const R* x, const R* y, const R* z, const R* u,
                     const R* v, const R* w, const R* rho, const R* m, const R* h, R* p, R* au, R* av,
                     R* aw, R* arho) {
-    wcsph_eos<R>(P, n, rho, p);
+    if (!P.p_given) wcsph_eos<R>(P, n, rho, p);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < n; ++i) {
         WcsphAcc<R> a{0, 0, 0, 0};
@@ -276,7 +278,7 @@ void wcsph_cells(const WcsphParams& P, const Grid& g, int64_t n, const R* x, con
                  R* av, R* aw, R* arho) {
     CellList<R> cl;
     cl.build(g, n, x, y, z);
-    wcsph_eos<R>(P, n, rho, p);
+    if (!P.p_given) wcsph_eos<R>(P, n, rho, p);
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < n; ++i) {
         WcsphAcc<R> a{0, 0, 0, 0};
@@ -309,7 +311,7 @@ void wcsph_step_sorted(const WcsphParams& P, const Grid& g, int64_t n, const R* 
         sx[s] = x[i]; sy[s] = y[i]; sz[s] = g.dim == 3 ? z[i] : (R)0;
         su[s] = u[i]; sv[s] = v[i]; sw[s] = g.dim == 3 ? w[i] : (R)0;
         sr[s] = rho[i]; sm[s] = m[i]; sh[s] = h[i];
-        sp[s] = tait_eos<R>(P, rho[i]);
+        sp[s] = P.p_given ? p[i] : tait_eos<R>(P, rho[i]);
     }
     // cell coordinates of sorted particle s are those of order[s]
 #pragma omp parallel for schedule(dynamic, 256)
@@ -338,6 +340,59 @@ void wcsph_step_sorted(const WcsphParams& P, const Grid& g, int64_t n, const R* 
         if (P.dim == 3) aw[i] = a.aw + (R)P.g[2];
         arho[i] = a.arho;
     }
+}
+
+// ----------------------------------------------------------------------------
+// Dummy-particle wall pressure (formulation: DESIGN.md 4d, after Adami, Hu & Adams 2012).
+// No reference code exists for it; this is the repo's own written contract.
+// For every NON-fluid particle w (tag != 0), over its FLUID neighbours f (tag == 0) under the neighbour rule of
+// Appendix A.1 with the support of w (0 < r2 < (kfac h_w)^2, same FMA-free arithmetic):
+//     S0 = sum W_wf,   Sp = sum p_f W_wf,   Sx = sum rho_f x_wf W_wf          (x_wf = x_w - x_f)
+//     p_w = (Sp + g . Sx) / S0  if S0 > 0 else 0       (wall acceleration a_w taken as 0: quasi-static walls)
+//     rho_w = rho0 (max(p_w / B, -1/2) + 1)^(1/gamma)  evaluated as rho0 exp(log1p(.) / gamma)
+// and p[w] = p_w, rho[w] = rho_w replace the EOS pressure and the state density of w: the pair loops then see the
+// extrapolated fluid pressure on dummy particles instead of one evolved by continuity.  Fluid rows are untouched.
+// W = Wendland C2 (Appendix A.2) with h = h_w.
+// ----------------------------------------------------------------------------
+template <class R>
+void wall_pressure(const WcsphParams& P, const Grid* g /* null => all pairs */, int64_t n, const R* x, const R* y,
+                   const R* z, const R* h, const int32_t* tag, R* rho /* in/out */, R* p /* in/out */) {
+    CellList<R> cl;
+    if (g) cl.build(*g, n, x, y, z);
+    const int dim = P.dim;
+    const R B = (R)(P.rho0 * P.c0 * P.c0 / P.gamma);
+    std::vector<R> pw(n), rw(n);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i) {
+        if (tag[i] == 0) continue;
+        const R hi = h[i];
+        const R rc = (R)P.kfac * hi;
+        const double pi = 3.14159265358979323846;
+        const R ad = dim == 3 ? (R)(21.0 / (16.0 * pi)) / (hi * hi * hi) : (R)(7.0 / (4.0 * pi)) / (hi * hi);
+        R S0 = 0, Sp = 0, Sx = 0, Sy = 0, Sz = 0;
+        auto body = [&](int64_t j) {
+            if (j == i || tag[j] != 0) return;
+            const R dx = x[i] - x[j], dy = y[i] - y[j], dz = dim == 3 ? z[i] - z[j] : (R)0;
+            const R r2 = dist2<R>(dim, dx, dy, dz);
+            if (!(r2 < rc * rc) || !(r2 > (R)0)) return;
+            const R q = std::sqrt(r2) / hi;
+            const R t = (R)1 - (R)0.5 * q;
+            const R t2 = t * t;
+            const R W = ad * (t2 * t2) * ((R)2 * q + (R)1);
+            S0 += W;
+            Sp += p[j] * W;
+            const R rW = rho[j] * W;
+            Sx += rW * dx; Sy += rW * dy; Sz += rW * dz;
+        };
+        if (g) cl.for_candidates(i, body);
+        else for (int64_t j = 0; j < n; ++j) body(j);
+        R pv = 0;
+        if (S0 > (R)0) pv = (Sp + ((R)P.g[0] * Sx + (R)P.g[1] * Sy + (R)P.g[2] * Sz)) / S0;
+        pw[i] = pv;
+        rw[i] = (R)P.rho0 * std::exp(std::log1p(std::max(pv / B, (R)-0.5)) / (R)P.gamma);
+    }
+    for (int64_t i = 0; i < n; ++i)
+        if (tag[i] != 0) { p[i] = pw[i]; rho[i] = rw[i]; }
 }
 
 // ----------------------------------------------------------------------------
@@ -477,7 +532,7 @@ int coupled_forces(const WcsphParams& PW, const DemParams& PD, const Grid* g /* 
                    R* hy_out, R* hz_out, R* fx, R* fy, R* fz, R* tx, R* ty, R* tz) {
     CellList<R> cl;
     if (g) cl.build(*g, n, x, y, z);
-    wcsph_eos<R>(PW, n, rho, p);
+    if (!PW.p_given) wcsph_eos<R>(PW, n, rho, p);
     int overflow = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(| : overflow)
     for (int64_t i = 0; i < n; ++i) {
@@ -543,6 +598,10 @@ ORC_API void orc_set_num_threads(int n) {
     }                                                                                                         \
     ORC_API void orc_wcsph_eos_##SFX(const WcsphParams* P, int64_t n, const R* rho, R* p) {                    \
         wcsph_eos<R>(*P, n, rho, p);                                                                          \
+    }                                                                                                         \
+    ORC_API void orc_wall_pressure_##SFX(const WcsphParams* P, const Grid* g, int64_t n, const R* x, const R* y, \
+                                         const R* z, const R* h, const int32_t* tag, R* rho, R* p) {           \
+        wall_pressure<R>(*P, g, n, x, y, z, h, tag, rho, p);                                                  \
     }                                                                                                         \
     ORC_API void orc_wcsph_allpairs_##SFX(const WcsphParams* P, int64_t n, const R* x, const R* y, const R* z, \
                                           const R* u, const R* v, const R* w, const R* rho, const R* m,       \

@@ -19,7 +19,7 @@ _LIB = None
 class WcsphParams(C.Structure):
     _fields_ = [("dim", C.c_int32), ("pad", C.c_int32), ("kfac", C.c_double), ("rho0", C.c_double),
                 ("c0", C.c_double), ("gamma", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
-                ("g", C.c_double * 3)]
+                ("g", C.c_double * 3), ("p_given", C.c_int32), ("pad2", C.c_int32)]
 
 
 class DemParams(C.Structure):
@@ -89,6 +89,7 @@ def wcsph_params(dim: int, P: dict) -> WcsphParams:
     w.kfac = P.get("kfac", 2.0)
     w.rho0, w.c0, w.gamma, w.alpha, w.beta = P["rho0"], P["c0"], P["gamma"], P["alpha"], P["beta"]
     w.g[0], w.g[1], w.g[2] = P.get("gx", 0.0), P.get("gy", 0.0), P.get("gz", 0.0)
+    w.p_given = 1 if P.get("_p_given") is not None else 0
     return w
 
 
@@ -135,12 +136,42 @@ def pairs(dim, x, y, z, s, mode=0, kfac=2.0, grid: Grid | None = None, cap=None)
     return pr, margin.value
 
 
+def wall_pressure(dim, P: dict, a: dict, p: np.ndarray, grid: Grid | None = None):
+    """Dummy-particle wall pressure (oracle.cpp wall_pressure): returns (rho, p) copies in which every
+    non-fluid row (tag != 0) holds the pressure extrapolated from its fluid neighbours and the density that the EOS
+    maps to it; fluid rows are unchanged."""
+    x = np.ascontiguousarray(a["x"]); n = len(x)
+    z = np.ascontiguousarray(a["z"]) if dim == 3 else np.zeros_like(x)
+    rho = np.array(a["rho"], dtype=x.dtype, copy=True); p = np.array(p, dtype=x.dtype, copy=True)
+    wp = wcsph_params(dim, P)
+    getattr(lib(), f"orc_wall_pressure_{_sfx(x)}")(C.byref(wp), C.byref(grid) if grid is not None else None, C.c_int64(n), _p(x),
+                                                   _p(np.ascontiguousarray(a["y"])), _p(z), _p(np.ascontiguousarray(a["h"])),
+                                                   _p(np.ascontiguousarray(a["tag"], np.int32)), _p(rho), _p(p))
+    return rho, p
+
+
+def _with_wall_pressure(dim, P: dict, a: dict, grid):
+    """boundary_model = 1: EOS, then wall_pressure; the pair loops get the modified rho and p as inputs."""
+    rho, p = wall_pressure(dim, P, a, eos(dim, P, np.ascontiguousarray(a["rho"])), grid)
+    a = dict(a)
+    a["rho"] = rho
+    return a, p
+
+
 def wcsph(dim, P: dict, a: dict, grid: Grid | None = None, sorted_step: bool = False):
-    """EOS + continuity + momentum.  Returns dict p, au, av, aw, arho in the input order."""
+    """EOS + continuity + momentum.  Returns dict p, au, av, aw, arho in the input order (+ "rho": the density the
+    pair loop saw, when P["boundary_model"] == 1 replaced the dummy particles' by the extrapolated one)."""
+    if int(P.get("boundary_model", 0)) == 1 and P.get("_p_given") is None:
+        a2, p = _with_wall_pressure(dim, P, a, grid)
+        out = wcsph(dim, dict(P, _p_given=p), a2, grid, sorted_step)
+        out["rho"] = a2["rho"]
+        return out
     x = np.ascontiguousarray(a["x"]); n = len(x); dt = x.dtype
     z = np.ascontiguousarray(a["z"]) if dim == 3 else np.zeros_like(x)
     w = np.ascontiguousarray(a["w"]) if dim == 3 else np.zeros_like(x)
     out = {k: np.zeros(n, dt) for k in ("p", "au", "av", "aw", "arho")}
+    if P.get("_p_given") is not None:
+        out["p"][:] = P["_p_given"]
     args = [_p(x), _p(np.ascontiguousarray(a["y"])), _p(z), _p(np.ascontiguousarray(a["u"])),
             _p(np.ascontiguousarray(a["v"])), _p(w), _p(np.ascontiguousarray(a["rho"])),
             _p(np.ascontiguousarray(a["m"])), _p(np.ascontiguousarray(a["h"])),
@@ -197,13 +228,22 @@ def sph_mass(a: dict, P: dict) -> np.ndarray:
 
 
 def coupled(P: dict, K: int, a: dict, hist: dict | None = None, ids: np.ndarray | None = None, grid: Grid | None = None):
-    """One coupled SPH-DEM force evaluation (3D).  Returns (rates + forces dict, new history dict, overflow flag)."""
+    """One coupled SPH-DEM force evaluation (3D).  Returns (rates + forces dict, new history dict, overflow flag).
+    P["boundary_model"] == 1: walls and solids carry the extrapolated fluid pressure (wall_pressure); out["rho"] is
+    the density the pair loop saw."""
+    if int(P.get("boundary_model", 0)) == 1 and P.get("_p_given") is None:
+        a2, p = _with_wall_pressure(3, P, a, grid)
+        out, new, ov = coupled(dict(P, _p_given=p), K, a2, hist, ids, grid)
+        out["rho"] = a2["rho"]
+        return out, new, ov
     x = np.ascontiguousarray(a["x"]); n = len(x); dt = x.dtype
     hist = hist or empty_history(n, K, dt)
     ids = np.arange(n, dtype=np.uint32) if ids is None else np.ascontiguousarray(ids, np.uint32)
     new = empty_history(n, K, dt)
     names_out = ("p", "au", "av", "aw", "arho", "fx", "fy", "fz", "tx", "ty", "tz")
     out = {k: np.zeros(n, dt) for k in names_out}
+    if P.get("_p_given") is not None:
+        out["p"][:] = P["_p_given"]
     ins = {k: np.ascontiguousarray(a[k], dt) for k in ("x", "y", "z", "u", "v", "w", "rho", "m", "h", "wx", "wy", "wz", "rad")}
     ins["ms"] = sph_mass(a, P)
     order = ("x", "y", "z", "u", "v", "w", "rho", "ms", "h", "wx", "wy", "wz", "rad", "m")
@@ -233,6 +273,8 @@ def coupled_integrate(a: dict, r: dict, P: dict, dt: float) -> dict:
     g = [T(P.get("gx", 0.0)), T(P.get("gy", 0.0)), T(P.get("gz", 0.0))]
     ratio = T(P["rho0"]) / T(P["rho_solid"])
     new["rho"] = a["rho"] + r["arho"] * dt
+    if int(P.get("boundary_model", 0)) == 1:        # dummy-particle density is slaved to the extrapolated pressure, not integrated
+        new["rho"] = np.where(fl, new["rho"], r["rho"] if "rho" in r else a["rho"])
     im = T(1) / a["m"]
     ii = T(1) / np.where(so, a["inertia"], T(1))
     for ax, (pos, vel, acc, frc, gk) in enumerate((("x", "u", "au", "fx", g[0]), ("y", "v", "av", "fy", g[1]), ("z", "w", "aw", "fz", g[2]))):

@@ -4,7 +4,7 @@ include/prestige_b200.h); this package is the host-side mirror of the reference 
 """
 from . import synth  # noqa: F401
 from .equations import (EquationIR, FusedEquations, body_reduce, continuity, debug_equation, dem_contact, eq1, equation, fuse,  # noqa: F401
-                        momentum, tait_eos)
+                        momentum, tait_eos, wall_pressure)
 from . import codegen, decomp, io  # noqa: F401
 from ._lib import PstError, LIB_PATH  # noqa: F401
 from .context import Context, context_for_block  # noqa: F401

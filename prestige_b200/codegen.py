@@ -23,7 +23,7 @@ class simple_cpu:
 
 
 class b200:
-    KERNELS = ("eq1", "tait_eos", "continuity", "momentum", "dem_contact", "body_reduce")
+    KERNELS = ("eq1", "tait_eos", "wall_pressure", "continuity", "momentum", "dem_contact", "body_reduce")
 
     @staticmethod
     def generate_b200(ir: FusedEquations) -> list:

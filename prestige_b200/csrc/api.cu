@@ -153,7 +153,8 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
     // default parameters
     ctx->params = {{"rho0", 1000.0}, {"c0", 10.0}, {"gamma", 7.0}, {"alpha", 0.1}, {"beta", 0.0}, {"kfac", 2.0},
                    {"gx", 0.0}, {"gy", 0.0}, {"gz", 0.0}, {"dem_model", 0.0}, {"kn", 1e5}, {"gn", 0.0}, {"kt", 2e4},
-                   {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}, {"rho_solid", 2500.0}};
+                   {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}, {"rho_solid", 2500.0},
+                   {"boundary_model", 0.0}};   // 1: dummy-particle wall pressure in pst_step, wall density slaved
     pst_status s = PST_OK;
     auto mk = [&](const char* name, int dt, uint32_t fl, int rows = 1) { if (s == PST_OK) s = array_create(ctx, name, dt, fl, rows); };
     const uint32_t P = PST_ARRAY_PERSISTENT, O = PST_ARRAY_OUTPUT;
@@ -195,7 +196,7 @@ void pst_destroy(pst_ctx* ctx) {
     pst_comm_destroy(ctx);
     for (auto& a : ctx->arrays) { cudaFree(a.buf[0]); if (a.buf[1]) cudaFree(a.buf[1]); }
     cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
-    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
+    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->wp_pos); cudaFree(ctx->wp_idx); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
     cudaFree(ctx->d_counters);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -470,7 +471,7 @@ pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
         if (!eq_names[k]) return PST_EINVAL;
         eqs.insert(eq_names[k]);
     }
-    static const std::set<std::string> known = {"eq1", "tait_eos", "continuity", "momentum", "dem_contact", "body_reduce"};
+    static const std::set<std::string> known = {"eq1", "tait_eos", "wall_pressure", "continuity", "momentum", "dem_contact", "body_reduce"};
     for (auto& e : eqs)
         if (!known.count(e)) return pst_fail(ctx, PST_EINVAL, "no hand-written kernel for equation '%s'", e.c_str());
     // fuse(): group the set into the fused kernels that exist.  Bodies that share an i,j loop
@@ -480,10 +481,15 @@ pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
         if (eqs.size() != 1) return pst_fail(ctx, PST_EINVAL, "eq1 cannot be fused with cutoff equations (it is an all-pairs loop)");
         return pst_eq1_apply(ctx);
     }
-    const bool wc = eqs.count("tait_eos") || eqs.count("continuity") || eqs.count("momentum");
+    const bool wc = eqs.count("tait_eos") || eqs.count("wall_pressure") || eqs.count("continuity") || eqs.count("momentum");
     if (wc && !(ctx->cfg.physics & PST_PHYS_WCSPH)) return pst_fail(ctx, PST_ESTATE, "context was created without PST_PHYS_WCSPH");
     if (eqs.count("dem_contact") && !(ctx->cfg.physics & PST_PHYS_DEM)) return pst_fail(ctx, PST_ESTATE, "context was created without PST_PHYS_DEM");
     if (eqs.count("tait_eos")) PST_TRY(pst_wcsph_eos(ctx));
+    if (eqs.count("wall_pressure")) {   // per dummy particle, a gather over its fluid neighbours: after the EOS, before the pair kernel reads p[j]
+        if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before wall_pressure");
+        if (!ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "wall_pressure reads p of the fluid: apply tait_eos first (or in the same set)");
+        PST_TRY(pst_wcsph_wall_pressure(ctx));
+    }
     if (eqs.count("continuity") || eqs.count("momentum")) {
         if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pair equations");
         if ((eqs.count("momentum") || ctx->coupled) && !ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "momentum reads p: apply tait_eos first (or in the same set)");
@@ -533,6 +539,7 @@ pst_status pst_step(pst_ctx* ctx, double dt, int n_steps) {
         if (ctx->comm) PST_TRY(pst_halo_exchange(ctx));
         if (ctx->cfg.physics & PST_PHYS_WCSPH) {
             PST_TRY(pst_wcsph_eos(ctx));
+            if (pst_param(ctx, "boundary_model", 0.0) == 1.0) PST_TRY(pst_wcsph_wall_pressure(ctx));
             PST_TRY(pst_wcsph_forces(ctx, true, true));
         }
         if (ctx->cfg.physics & PST_PHYS_DEM) {

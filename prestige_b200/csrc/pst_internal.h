@@ -68,6 +68,7 @@ struct pst_ctx {
     int32_t *nf_pos = nullptr, *nf_idx = nullptr;   // coupled contexts: compacted non-fluid particles of the sorted order (dem.cu)
     void* nf_rec = nullptr;                         // their (x, y, z, rad) records
     bool nf_dirty = true;                           // force rows of non-spheres are not known to be zero
+    int32_t *wp_pos = nullptr, *wp_idx = nullptr;   // wall_pressure: compacted non-fluid particles of the owned range (wcsph.cu)
     uint32_t* big_list() const { return keys_out; }   // crowded-cell list reuses keys_out (unused by the counting sort)
     size_t sort_tmp_bytes = 0;
     char* stage = nullptr;           // capacity * 8 bytes
@@ -144,6 +145,7 @@ pst_status pst_reorder_download(pst_ctx* ctx, PstArray* a, int row, size_t n); /
 pst_status pst_iota_ids(pst_ctx* ctx);
 pst_status pst_eq1_apply(pst_ctx* ctx);                                   // eq1.cu
 pst_status pst_wcsph_eos(pst_ctx* ctx);                                   // wcsph.cu
+pst_status pst_wcsph_wall_pressure(pst_ctx* ctx);                         // dummy-particle pressure extrapolation (after the EOS)
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum);
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu

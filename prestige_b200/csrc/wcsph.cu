@@ -229,8 +229,16 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
     size_t off = ((size_t)(NR * W + NR + NR + 1 + NI + NI + 1) * sizeof(int) + 15) & ~(size_t)15;
     double* s_org = reinterpret_cast<double*>(smem_raw + off);   // 3 (+1 pad): tile origin
     off += 4 * sizeof(double);
+#if !defined(PST_P1_AOS)   // default: candidates staged as SoA rows so phase 1 runs packed f32x2 arithmetic (-DPST_P1_AOS: the float4 layout, A/B)
+    float* s_x = reinterpret_cast<float*>(smem_raw + off);
+    float* s_y = s_x + JC;
+    float* s_z = s_y + JC;
+    int* s_gj = reinterpret_cast<int*>(s_z + JC);
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_gj + JC);   // lcap * NT
+#else
     float4* s_p4 = reinterpret_cast<float4*>(smem_raw + off);
     unsigned short* s_list = reinterpret_cast<unsigned short*>(s_p4 + JC);   // lcap * NT
+#endif
 
     const int tid = threadIdx.x;
     // ---- which tile
@@ -310,7 +318,12 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
         p.x = (float)(A.x[gj] - ox); p.y = (float)(A.y[gj] - oy); p.z = DIM == 3 ? (float)(A.z[gj] - oz) : 0.0f;
         p.w = __int_as_float(gj);
         if (LOCAL) far |= fabsf(p.x) > far_lim || fabsf(p.y) > far_lim || fabsf(p.z) > far_lim;
+#if !defined(PST_P1_AOS)
+        s_x[v] = p.x; s_y[v] = p.y; if (DIM == 3) s_z[v] = p.z;
+        s_gj[v] = gj;
+#else
         s_p4[v] = p;
+#endif
     }
     far = __syncthreads_or(far);
 
@@ -343,6 +356,24 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
             r2f = dist2<DIM, float>(dxf, dyf, dzf);
             return r2f < rc2f && r2f > 0.0f;
         };
+#if !defined(PST_P1_AOS)
+        // two candidates per instruction: FADD2 / FMUL2 / FFMA2 on register pairs (x_k, x_k+1) as LDS.128 delivers them
+        const float2 xf2 = make_float2(xf, xf), yf2 = make_float2(yf, yf), zf2 = make_float2(zf, zf);
+        auto r2_pair = [&](float xa, float xb, float ya, float yb, float za, float zb) -> float2 {
+            const float2 dx = __fadd2_rn(xf2, make_float2(-xa, -xb)), dy = __fadd2_rn(yf2, make_float2(-ya, -yb));
+            const float2 dz = DIM == 3 ? __fadd2_rn(zf2, make_float2(-za, -zb)) : make_float2(0.0f, 0.0f);
+            if (LOCAL) {
+                float2 r = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+                if (DIM == 3) r = __ffma2_rn(dz, dz, r);
+                return r;
+            }
+            float2 r = __fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy));     // exact test of f32 contexts: left to right, no FMA
+            if (DIM == 3) r = __fadd2_rn(r, __fmul2_rn(dz, dz));
+            return r;
+        };
+        auto hit = [&](float r2f) -> bool { return LOCAL ? r2f <= rc2f : (r2f < rc2f && r2f > 0.0f); };
+        auto test_at = [&](int j) -> bool { return test(make_float4(s_x[j], s_y[j], DIM == 3 ? s_z[j] : 0.0f, 0.0f)); };
+#endif
         // scan cursor over this particle's 9 (3) runs
         int run = 0, jv = 0, jend = 0;
         constexpr int NRUN = DIM == 3 ? 9 : 3;
@@ -366,6 +397,27 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
                 // barrier after the scan orders the list stores before phase 2 reads them)
                 auto push = [&](int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(la), "h"((unsigned short)v)); la += 2 * NT; };
                 while (true) {
+#if !defined(PST_P1_AOS)
+                    while ((jv & 3) && jv < jend && la < lend) {             // head: up to the next 16-byte boundary of the SoA rows
+                        if (test_at(jv)) push(jv);
+                        ++jv;
+                    }
+                    while (jv + 4 <= jend && la + 8 * NT <= lend) {          // 4 candidates = 3 LDS.128 + 2 x (3 FADD2, FMUL2, 2 FFMA2)
+                        const float4 X = *reinterpret_cast<const float4*>(s_x + jv), Y = *reinterpret_cast<const float4*>(s_y + jv);
+                        const float4 Z = DIM == 3 ? *reinterpret_cast<const float4*>(s_z + jv) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        const float2 ra = r2_pair(X.x, X.y, Y.x, Y.y, Z.x, Z.y), rb = r2_pair(X.z, X.w, Y.z, Y.w, Z.z, Z.w);
+                        const bool h0 = hit(ra.x), h1 = hit(ra.y), h2 = hit(rb.x), h3 = hit(rb.y);
+                        if (h0) push(jv);
+                        if (h1) push(jv + 1);
+                        if (h2) push(jv + 2);
+                        if (h3) push(jv + 3);
+                        jv += 4;
+                    }
+                    while (jv < jend && la < lend) {
+                        if (test_at(jv)) push(jv);
+                        ++jv;
+                    }
+#else
                     while (jv + 4 <= jend && la + 8 * NT <= lend) {          // 4 candidates in flight
                         const float4 p0 = s_p4[jv], p1 = s_p4[jv + 1], p2 = s_p4[jv + 2], p3 = s_p4[jv + 3];
                         const bool h0 = test(p0), h1 = test(p1), h2 = test(p2), h3 = test(p3);
@@ -379,6 +431,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
                         if (test(s_p4[jv])) push(jv);
                         ++jv;
                     }
+#endif
                     if (jv < jend) break;          // list full: drain, then resume here
                     if (++run == NRUN) { done = true; break; }
                     open_run(run);
@@ -389,8 +442,13 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
             // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
             for (int k = 0; k < cnt; k += 2) {
                 const bool v1 = k + 1 < cnt;
+#if !defined(PST_P1_AOS)
+                const int j0 = s_gj[my_list[k * NT]];
+                const int j1 = v1 ? s_gj[my_list[(k + 1) * NT]] : j0;
+#else
                 const int j0 = __float_as_int(s_p4[my_list[k * NT]].w);
                 const int j1 = v1 ? __float_as_int(s_p4[my_list[(k + 1) * NT]].w) : j0;
+#endif
 #if defined(PST_EXP_SMEM)    // timing experiment only (wrong results): the 9 gathers come from shared memory
                 auto LD = [&](const R*, int j, int f) -> R { return (R)reinterpret_cast<const double*>(s_p4)[(j * 9 + f) & 2047]; };
 #else
@@ -772,15 +830,17 @@ pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
 
 // semi-implicit Euler stage: fluid (tag 0): v += a dt, x += v dt;
 // every particle: rho += arho dt.  Boundary particles (tag 1) keep position and velocity.
+// `slaved` (boundary_model = 1): the density of non-fluid particles is set by wall_pressure, not integrated.
 template <class R, int DIM>
-__global__ void __launch_bounds__(256) k_integrate(int n, R dt, const int32_t* __restrict__ tag, R* __restrict__ x, R* __restrict__ y,
+__global__ void __launch_bounds__(256) k_integrate(int n, R dt, bool slaved, const int32_t* __restrict__ tag, R* __restrict__ x, R* __restrict__ y,
                                                    R* __restrict__ z, R* __restrict__ u, R* __restrict__ v, R* __restrict__ w,
                                                    R* __restrict__ rho, const R* __restrict__ au, const R* __restrict__ av,
                                                    const R* __restrict__ aw, const R* __restrict__ arho) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    rho[s] += arho[s] * dt;
-    if (tag[s] != 0) return;
+    const bool fluid = tag[s] == 0;
+    if (fluid || !slaved) rho[s] += arho[s] * dt;
+    if (!fluid) return;
     const R un = u[s] + au[s] * dt, vn = v[s] + av[s] * dt;
     u[s] = un; v[s] = vn;
     x[s] += un * dt; y[s] += vn * dt;
@@ -794,7 +854,7 @@ __global__ void __launch_bounds__(256) k_integrate(int n, R dt, const int32_t* _
 template <class R, int DIM, bool MORTON>
 pst_status launch_integrate(pst_ctx* ctx, double dt) {
     const int n = (int)ctx->n;
-    PST_LAUNCH(ctx, (k_integrate<R, DIM>), blocks_for(n, 256), 256, 0, n, (R)dt, pst_ptr<int32_t>(ctx, "tag"), pst_ptr<R>(ctx, "x"),
+    PST_LAUNCH(ctx, (k_integrate<R, DIM>), blocks_for(n, 256), 256, 0, n, (R)dt, pst_param(ctx, "boundary_model", 0.0) == 1.0, pst_ptr<int32_t>(ctx, "tag"), pst_ptr<R>(ctx, "x"),
                pst_ptr<R>(ctx, "y"), pst_ptr<R>(ctx, "z"), pst_ptr<R>(ctx, "u"), pst_ptr<R>(ctx, "v"), pst_ptr<R>(ctx, "w"),
                pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "au"), pst_ptr<R>(ctx, "av"), pst_ptr<R>(ctx, "aw"), pst_ptr<R>(ctx, "arho"));
     return PST_OK;
@@ -811,14 +871,15 @@ struct CoupledIntArgs {
     const R *m, *inertia, *au, *av, *aw, *arho, *fx, *fy, *fz, *tx, *ty, *tz;
     R dt, g[3], ratio;
     int n;
+    bool slaved;   // boundary_model = 1: the density of non-fluid particles is set by wall_pressure, not integrated
 };
 template <class R>
 __global__ void __launch_bounds__(256) k_coupled_integrate(CoupledIntArgs<R> A) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.n) return;
     const R dt = A.dt;
-    A.rho[s] += A.arho[s] * dt;
     const int t = A.tag[s];
+    if (t == 0 || !A.slaved) A.rho[s] += A.arho[s] * dt;
     if (t == 1) return;
     R ax = A.au[s], ay = A.av[s], az = A.aw[s];
     if (t == 2) {
@@ -848,6 +909,7 @@ pst_status launch_coupled_integrate(pst_ctx* ctx, double dt) {
     A.g[0] = (R)pst_param(ctx, "gx"); A.g[1] = (R)pst_param(ctx, "gy"); A.g[2] = (R)pst_param(ctx, "gz");
     A.ratio = (R)pst_param(ctx, "rho0") / (R)pst_param(ctx, "rho_solid", 1.0);
     A.n = (int)ctx->n;
+    A.slaved = pst_param(ctx, "boundary_model", 0.0) == 1.0;
     PST_LAUNCH(ctx, k_coupled_integrate<R>, blocks_for(A.n, 256), 256, 0, A);
     return PST_OK;
 }
@@ -864,7 +926,100 @@ pst_status launch_eos(pst_ctx* ctx) {
     return PST_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dummy-particle wall pressure (after Adami, Hu & Adams 2012).  No reference code exists
+// for it; the formulation is restated in oracle/oracle.cpp:wall_pressure.  For every NON-fluid particle w (tag != 0),
+// over its FLUID neighbours f (A.1 rule with the support of w):
+//     S0 = sum W_wf,  Sp = sum p_f W_wf,  S = sum rho_f x_wf W_wf,   p_w = (Sp + g . S) / S0  (0 without fluid neighbours)
+//     rho_w = rho0 (max(p_w / B, -1/2) + 1)^(1/gamma)
+// and p, p/rho^2 and the STATE density of w are overwritten, so the fused pair kernel runs unchanged: it simply gathers
+// the extrapolated values for dummy neighbours.  Runs after k_eos (reads p of fluid rows, writes non-fluid rows: no race).
+//   k_wp_flags -> in-place exclusive scan (the counting sort's scan kernels) -> k_wp_fill: the non-fluid particles of the
+//   owned range, compacted in sorted order, so k_wall_pressure runs full warps of neighbouring dummy particles (their
+//   candidate runs overlap: L1 hits) instead of one warp in ten lanes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wp_flags(int n, const int32_t* __restrict__ tag, int32_t* __restrict__ pos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    pos[s] = s < n && tag[s] != 0;
+}
+
+__global__ void __launch_bounds__(256) k_wp_fill(int n, const int32_t* __restrict__ tag, const int32_t* __restrict__ pos, int32_t* __restrict__ idx) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n && tag[s] != 0) idx[pos[s]] = s;
+}
+
+template <class R, int DIM, bool MORTON>
+__global__ void __launch_bounds__(kThreads) k_wall_pressure(GridDev<R> g, WcsphConst<R> C, int n, const int32_t* __restrict__ pos,
+                                                            const int32_t* __restrict__ idx, const int32_t* __restrict__ tag,
+                                                            const R* __restrict__ x, const R* __restrict__ y, const R* __restrict__ z,
+                                                            const R* __restrict__ h, R* rho, R* p, R* __restrict__ por2,
+                                                            const int32_t* __restrict__ cell_start) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pos[n]) return;                 // pos[n] = number of non-fluid particles (device-side count, no host sync)
+    const int s = idx[t];
+    const R xi = x[s], yi = y[s], zi = DIM == 3 ? z[s] : (R)0, hi = h[s];
+    const R pi = (R)3.14159265358979323846;
+    const R ad = DIM == 3 ? (R)(21.0 / 16.0) / (pi * hi * hi * hi) : (R)(7.0 / 4.0) / (pi * hi * hi);
+    const R inv_h = (R)1 / hi;
+    const R rc = mul_rn(C.kfac, hi);
+    const R rc2 = mul_rn(rc, rc);
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    R S0 = 0, Sp = 0, Sx = 0, Sy = 0, Sz = 0;
+    for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
+        for (int j = b; j < e; ++j) {
+            const R dx = xi - x[j], dy = yi - y[j], dz = DIM == 3 ? zi - z[j] : (R)0;
+            const R r2 = dist2<DIM, R>(dx, dy, dz);
+            if (r2 < rc2 && r2 > (R)0 && tag[j] == 0) {
+                const R q = r2 * fast_rsqrt(r2) * inv_h;
+                const R tt = (R)1 - (R)0.5 * q;
+                const R t2 = tt * tt;
+                const R W = ad * (t2 * t2) * ((R)2 * q + (R)1);
+                S0 += W;
+                Sp += p[j] * W;
+                const R rW = rho[j] * W;
+                Sx += rW * dx; Sy += rW * dy;
+                if (DIM == 3) Sz += rW * dz;
+            }
+        }
+    });
+    R pv = (R)0;
+    if (S0 > (R)0) pv = (Sp + (C.g[0] * Sx + C.g[1] * Sy + C.g[2] * Sz)) / S0;
+    const R rw = C.rho0 * exp(log1p(max(pv / C.B, (R)-0.5)) / C.gamma);
+    p[s] = pv;
+    rho[s] = rw;
+    por2[s] = pv / (rw * rw);
+}
+
+template <class R, int DIM, bool MORTON>
+pst_status launch_wall_pressure(pst_ctx* ctx) {
+    const int n = (int)ctx->n;
+    const int32_t* tag = pst_ptr<int32_t>(ctx, "tag");
+    if (!tag) return pst_fail(ctx, PST_ESTATE, "wall_pressure needs the tag array");
+    if (!ctx->wp_pos) {
+        const size_t cap = ctx->capacity + 2;
+        if (cudaMalloc((void**)&ctx->wp_pos, cap * 4) != cudaSuccess || cudaMalloc((void**)&ctx->wp_idx, cap * 4) != cudaSuccess)
+            return pst_fail(ctx, PST_ENOMEM, "wall_pressure compaction buffers");
+    }
+    PST_LAUNCH(ctx, k_wp_flags, blocks_for(n + 1, 256), 256, 0, n, tag, ctx->wp_pos);
+    PST_TRY(pst_scan_exclusive(ctx, ctx->wp_pos, n + 1));
+    PST_LAUNCH(ctx, k_wp_fill, blocks_for(n, 256), 256, 0, n, tag, ctx->wp_pos, ctx->wp_idx);
+    // the grid covers the worst case (every particle a dummy); threads beyond the device-side count exit at once
+    PST_LAUNCH(ctx, (k_wall_pressure<R, DIM, MORTON>), blocks_for(n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), n,
+               ctx->wp_pos, ctx->wp_idx, tag, pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), pst_ptr<R>(ctx, "z"), pst_ptr<R>(ctx, "h"),
+               pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "p"), pst_ptr<R>(ctx, "por2"), ctx->cell_start);
+    return PST_OK;
+}
+
 }  // namespace
+
+pst_status pst_wcsph_wall_pressure(pst_ctx* ctx) {
+    if (ctx->n == 0) return PST_OK;
+    if (ctx->comm) return pst_fail(ctx, PST_EINVAL, "wall_pressure is single-GPU for now: ghost dummy particles would need a second density exchange");
+    return PST_DISPATCH(ctx, launch_wall_pressure, ctx);
+}
 
 pst_status pst_wcsph_eos(pst_ctx* ctx) {
     PST_TRY(ctx->f64 ? launch_eos<double>(ctx) : launch_eos<float>(ctx));

@@ -144,6 +144,10 @@ momentum = declare("momentum", ["x", "y", "z", "u", "v", "w", "m", "h", "rho", "
 dem_contact = declare("dem_contact", ["x", "y", "z", "u", "v", "w", "wx", "wy", "wz", "rad", "m", "hist_id", "hist_x", "hist_y", "hist_z", "hist_n"],
                       ["fx", "fy", "fz", "tx", "ty", "tz", "hist_id", "hist_x", "hist_y", "hist_z", "hist_n"],
                       "{ (F[i], T[i], xi[i][j]) += spring_dashpot(x_ij, v_ij, w, rad, xi[i][j]) ; }")
+# gather over the FLUID neighbours of every dummy (non-fluid) particle: extrapolated pressure and the density the EOS maps
+# to it.  Applied after tait_eos; the pair equations then read the extrapolated values.
+wall_pressure = declare("wall_pressure", ["x", "y", "z", "h", "tag", "rho", "p"], ["p", "rho"],
+                        "{ if tag[i] != 0 && tag[j] == 0 { num[i] += (p[j] + rho[j] * dot(g, x_ij)) * w(x_ij, h[i]) ; den[i] += w(x_ij, h[i]) ; } }")
 # per-particle (no j): sums the force loop's results over the members of each rigid body
 body_reduce = declare("body_reduce", ["x", "y", "z", "m", "body", "fx", "fy", "fz", "tx", "ty", "tz", "au", "av", "aw"],
                       ["body_force", "body_torque"],

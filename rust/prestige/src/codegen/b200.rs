@@ -22,7 +22,7 @@ pub struct B200Context {
     n: usize,
 }
 
-const KERNELS: [&str; 6] = ["eq1", "tait_eos", "continuity", "momentum", "dem_contact", "body_reduce"];
+const KERNELS: [&str; 7] = ["eq1", "tait_eos", "wall_pressure", "continuity", "momentum", "dem_contact", "body_reduce"];
 
 impl B200Context {
     pub fn new(cfg: &sys::pst_config) -> Result<Self, B200Error> {

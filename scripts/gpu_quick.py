@@ -17,6 +17,7 @@ import __graft_entry__ as G  # noqa: E402
 import test_coupled as TC  # noqa: E402
 import test_gpu_parity as TP  # noqa: E402
 import test_rigid as TR  # noqa: E402
+import test_wall_pressure as TW  # noqa: E402
 
 f64, f32 = np.float64, np.float32
 tmp = lambda: Path(tempfile.mkdtemp())
@@ -46,6 +47,11 @@ CASES = [
     ("coupled_step_vs_host", TC.test_coupled_step_matches_host_integration),
     ("rigid_setup_reduce", lambda: TR.test_rigid_setup_reduce_parity_gpu(f64)),
     ("rigid_checkpoint", lambda: TR.test_rigid_checkpoint_resume_bit_exact_gpu(tmp())),
+    ("wall_wcsph_f64_linear", lambda: TW.test_wall_pressure_gpu_wcsph(f64, "linear")),
+    ("wall_wcsph_f32_morton", lambda: TW.test_wall_pressure_gpu_wcsph(f32, "morton")),
+    ("wall_coupled_f64", lambda: TW.test_wall_pressure_gpu_coupled(f64)),
+    ("wall_coupled_f32", lambda: TW.test_wall_pressure_gpu_coupled(f32)),
+    ("wall_step_errors", TW.test_wall_pressure_step_and_errors),
 ]
 if len(sys.argv) > 1:
     CASES = [c for c in CASES if c[0] in sys.argv[1:]]

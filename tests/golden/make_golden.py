@@ -40,3 +40,9 @@ ct, _ = orc.pairs(3, k.arrays["x"], k.arrays["y"], k.arrays["z"], k.arrays["rad"
 ct = ct[(tag[ct[:, 0]] == 2) & (tag[ct[:, 1]] != 0)]
 np.savez_compressed(os.path.join(HERE, "coupled3d_small.npz"), x=k.arrays["x"], tag=tag, neighbours=nb, contacts=ct, hist_n=h2["hist_n"], **r2)
 print("coupled golden vectors written")
+
+# dummy-particle wall pressure: the small dam break with boundary_model = 1 (p, slaved wall density, rates)
+c = synth.wcsph_dambreak_2d(dx=0.05).shuffled()
+r = orc.wcsph(2, dict(c.params, boundary_model=1), c.arrays)
+np.savez_compressed(os.path.join(HERE, "wall2d_small.npz"), **r)
+print("wall pressure golden vectors written")
