@@ -4,14 +4,17 @@
 // the loop shape -- gather into [i], bodies of a fused set share one i,j loop
 // (prestige/src/codegen/simple_cpu.rs:7-16, prestige/src/equations/fuse.rs:14-40).
 //
-// Two pair kernels, both computing continuity and/or momentum in ONE j loop:
-//   k_wcsph_gather  one thread per particle, walks its 9 (3D) / 3 (2D) contiguous candidate runs
-//                   straight from global memory.  Any key mode, any occupancy.  (option force_kernel=0)
-//   k_wcsph_tiled   one CTA per tile of A x B cell columns x G cells along the fast axis.  The
-//                   (A+2)(B+2) candidate runs are staged ONCE in shared memory (coalesced loads of the
-//                   sorted SoA arrays), then every thread (a) scans its candidates with the exact,
-//                   FMA-free cutoff test and compacts the hits into a private list, (b) evaluates the
-//                   expensive pair body only for the hits, with all lanes busy.  Linear keys only.
+// Three pair kernels (option force_kernel), all computing continuity and/or momentum in ONE j loop:
+//   0 k_wcsph_gather    one thread per particle, walks its 9 (3D) / 3 (2D) contiguous candidate runs
+//                       straight from global memory.  Any key mode, any occupancy.
+//   1 k_wcsph_cellwarp  one warp per cell, candidates cached in registers, hits ballot-compacted.  Linear keys.
+//   2 k_wcsph_tiled     (default) one CTA per tile of A x B cell columns x G cells along the fast axis.  The
+//                       (A+2)(B+2) candidate runs are staged ONCE in shared memory (coalesced loads of the
+//                       sorted SoA arrays) as f32 coordinates + index, then every thread (a) scans its candidates
+//                       (packed f32x2 arithmetic; a conservative pre-filter in f64 contexts) and compacts the hits
+//                       into a private list, (b) evaluates the expensive pair body only for the hits -- the exact,
+//                       FMA-free cutoff test decides there -- with all lanes busy.  Linear keys only.
+// Also here: the EOS, the dummy-particle wall pressure (k_wall_pressure) and the semi-implicit Euler stages.
 #include "pst_internal.h"
 
 namespace {
@@ -185,11 +188,12 @@ __global__ void __launch_bounds__(kThreads) k_wcsph_gather(GridDev<R> g, WcsphCo
 // ---------------------------------------------------------------------------------------------
 // variant 2: shared-memory tiles, ONE THREAD PER PARTICLE, private hit lists
 //
-//   * staged per tile: only a float4 per candidate -- f32 coordinates (tile-local for f64 contexts) and, in .w,
-//     the candidate's global index.  16 B instead of 72 B per candidate leaves room for two CTAs per SM;
-//   * phase 1: each thread scans its 9 (3) runs with one LDS.128 and ~7 FP32 instructions per candidate
-//     (4 candidates in flight), appending hits to its private 16-bit list.  For f64 contexts this is a
-//     CONSERVATIVE pre-filter (margin 2^-15, switched off for tiles holding far-away particles);
+//   * staged per tile: 16 B per candidate -- f32 coordinates (tile-local for f64 contexts) and the candidate's
+//     global index, as four SoA rows x[] y[] z[] index[] (-DPST_P1_AOS: one float4 per candidate, the layout the
+//     packed form was measured against).  16 B instead of 72 B per candidate leaves room for two CTAs per SM;
+//   * phase 1: each thread scans its 9 (3) runs four candidates at a time: 3 LDS.128 + 6 FADD2 + 2 FMUL2 + 4 FFMA2
+//     (sm_100a f32x2: two candidates per instruction) + 4 FSETP, appending hits to its private 16-bit list.  For
+//     f64 contexts this is a CONSERVATIVE pre-filter (margin 2^-15, switched off for tiles holding far-away particles);
 //   * phase 2: two hits per trip; the f64 state of j is gathered straight from global memory -- L1/L2 hits, since
 //     the CTA's threads share the same ~1300 candidates and staging has just touched them -- the exact
 //     FMA-free cutoff test decides membership, then the branch-free pair body runs.
@@ -449,6 +453,9 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
                 const int j0 = __float_as_int(s_p4[my_list[k * NT]].w);
                 const int j1 = v1 ? __float_as_int(s_p4[my_list[(k + 1) * NT]].w) : j0;
 #endif
+#if defined(PST_EXP_SMEM) && !defined(PST_P1_AOS)
+#error "PST_EXP_SMEM (timing experiment) reads the float4 staging buffer: build it together with -DPST_P1_AOS"
+#endif
 #if defined(PST_EXP_SMEM)    // timing experiment only (wrong results): the 9 gathers come from shared memory
                 auto LD = [&](const R*, int j, int f) -> R { return (R)reinterpret_cast<const double*>(s_p4)[(j * 9 + f) & 2047]; };
 #else
@@ -479,9 +486,9 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
 
 
 // ---------------------------------------------------------------------------------------------
-// variant 2 (default): shared-memory tiles, ONE WARP PER CELL, candidate-parallel scan
+// variant 1: shared-memory tiles, ONE WARP PER CELL, candidate-parallel scan
 //
-//   * tile staging as in variant 1 (the (A+2)(B+2) candidate runs, coalesced, once per CTA);
+//   * tile staging of the full f64 neighbour state (the (A+2)(B+2) candidate runs, coalesced, once per CTA);
 //   * a warp takes one cell at a time.  All particles of a cell share the same 9 (3) candidate runs,
 //     so the warp flattens them ONCE into a per-lane register cache: lane l holds candidates
 //     l, l+32, l+64, ... as f32 coordinates (tile-local for f64 contexts) plus their staged index;
