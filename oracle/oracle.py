@@ -109,10 +109,6 @@ def eq1_allpairs(mass: np.ndarray, force: np.ndarray) -> np.ndarray:
     return force
 
 
-def _zeros_like_opt(a, dim):
-    return a if a is not None else None
-
-
 def pairs(dim, x, y, z, s, mode=0, kfac=2.0, grid: Grid | None = None, cap=None):
     """Neighbour (mode 0, s = h) or contact (mode 1, s = radius) set as an (n_pairs, 2) uint32 array
     sorted lexicographically.  grid=None -> all-pairs (truth); else cell list.  Also returns the

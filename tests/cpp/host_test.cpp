@@ -33,6 +33,11 @@ static int test_fusion() {
     CHECK(code == "for i in 0..n {\n    for j in 0..n {\n        { force [i] += mass [j] ; }\n    }\n}\n");
     auto plan = codegen::b200::generate_b200(fuse({tait_eos::ir(), continuity::ir(), momentum::ir()}));
     CHECK(plan.size() == 3 && plan[1] == "continuity");
+    auto walled = fuse({tait_eos::ir(), wall_pressure::ir(), continuity::ir(), momentum::ir()});
+    CHECK(codegen::b200::generate_b200(walled).size() == 4 && walled.names[1] == "wall_pressure");
+    bool writes_rho = false;
+    for (const auto& w : walled.writes) writes_rho = writes_rho || w == "rho";      // the equation slaves the dummy density
+    CHECK(writes_rho);
     bool threw = false;
     try { codegen::b200::generate_b200(fuse({{"nope", {}, {}, "{}"}})); } catch (const std::invalid_argument&) { threw = true; }
     CHECK(threw);

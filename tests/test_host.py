@@ -53,6 +53,16 @@ def test_macro_semantics():
 def test_b200_backend_plan():
     f = pb.fuse([pb.tait_eos.ir(), pb.continuity.ir(), pb.momentum.ir()])
     assert pb.codegen.b200.generate_b200(f) == ["tait_eos", "continuity", "momentum"]
+    w = pb.fuse([pb.tait_eos.ir(), pb.wall_pressure.ir(), pb.continuity.ir(), pb.momentum.ir()])
+    assert pb.codegen.b200.generate_b200(w)[1] == "wall_pressure" and {"p", "rho"} <= set(w.writes)
+    # every name the back-ends list has a kernel behind pst_apply (api.cu) and vice versa
+    api = open(os.path.join(ROOT, "prestige_b200", "csrc", "api.cu")).read()
+    known = re.search(r"known = \{([^}]*)\}", api).group(1)
+    assert sorted(re.findall(r'"(\w+)"', known)) == sorted(pb.codegen.b200.KERNELS)
+    hpp = open(os.path.join(ROOT, "include", "prestige.hpp")).read()
+    assert sorted(re.findall(r'"(\w+)"', re.search(r"kernels = \{([^}]*)\}", hpp).group(1))) == sorted(pb.codegen.b200.KERNELS)
+    rs = open(os.path.join(ROOT, "rust", "prestige", "src", "codegen", "b200.rs")).read()
+    assert sorted(re.findall(r'"(\w+)"', re.search(r"KERNELS: \[&str; \d+\] = \[([^\]]*)\]", rs).group(1))) == sorted(pb.codegen.b200.KERNELS)
     with pytest.raises(ValueError):
         @pb.equation
         def unknown(i, j, q):

@@ -98,8 +98,8 @@ def test_coupled_wall_pressure_oracle():
     assert (ra["p"][tag != 0] != r0["p"][tag != 0]).any()
     # pairwise antisymmetry survives: both sides of a fluid-dummy pair read the same extrapolated pressure
     P0 = dict(P, gz=0.0)
-    r, _, _ = orc.coupled(P0, b.max_contacts, synth.coupled_block_3d(12, 10, 12, floor=False).shuffled().arrays)
     bb = synth.coupled_block_3d(12, 10, 12, floor=False).shuffled()
+    r, _, _ = orc.coupled(P0, bb.max_contacts, bb.arrays)
     ms = orc.sph_mass(bb.arrays, P0)
     for acc, f in (("au", "fx"), ("av", "fy"), ("aw", "fz")):
         tot = (ms * r[acc]).sum() + r[f].sum()
