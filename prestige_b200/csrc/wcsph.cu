@@ -16,17 +16,12 @@
 //                       FMA-free cutoff test decides there -- with all lanes busy.  Linear keys only.
 // Also here: the EOS, the dummy-particle wall pressure (k_wall_pressure) and the semi-implicit Euler stages.
 #include "pst_internal.h"
+#include "wcsph_core.h"   // WcsphConst, IState, Acc, load_i, pair_body, wall_accumulate / wall_finish (shared with the host test harness)
 
 namespace {
 
 constexpr int kThreads = 128;
 inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
-
-template <class R>
-struct WcsphConst {
-    R kfac, rho0, c0, gamma, B, alpha_c0, beta, g[3];
-    int gamma_is_7;
-};
 
 template <class R>
 WcsphConst<R> make_const(pst_ctx* ctx) {
@@ -65,71 +60,6 @@ __global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, co
     const R pr = C.B * expm1(C.gamma * log1p(e));
     p[s] = pr;
     por2[s] = pr / (r * r);
-}
-
-// ---------------------------------------------------------------------------------------------
-// the pair body (continuity then momentum, the order fuse() keeps: fuse.rs:18,30)
-// ---------------------------------------------------------------------------------------------
-template <class R, int DIM>
-struct IState {         // everything about particle i the body needs, in registers
-    R x, y, z, u, v, w, rho, por2, h, half_inv_h, gfc, eta2, rc2;
-};
-template <class R>
-struct Acc { R au, av, aw, arho; };
-
-template <class R, int DIM>
-__device__ __forceinline__ void load_i(IState<R, DIM>& I, const WcsphConst<R>& C, R x, R y, R z, R u, R v, R w, R rho, R por2, R h) {
-    I.x = x; I.y = y; I.z = z; I.u = u; I.v = v; I.w = w; I.rho = rho; I.por2 = por2; I.h = h;
-    I.half_inv_h = (R)0.5 / h;
-    const R pi = (R)3.14159265358979323846;
-    const R ad = DIM == 3 ? (R)(21.0 / 16.0) / (pi * h * h * h) : (R)(7.0 / 4.0) / (pi * h * h);
-    I.gfc = (R)-5 * ad / (h * h);       // (dW/dq)/(h r) = gfc * (1 - q/2)^3
-    I.eta2 = (R)0.01 * h * h;
-    const R rc = mul_rn(C.kfac, h);
-    I.rc2 = mul_rn(rc, rc);
-}
-
-// 1/sqrt(x) and 1/x for normal positive x: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) + ONE cubically
-// convergent correction, no special-case branches.  Error ~2 ulp (e^3 ~ 2^-66 is below the rounding).
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2
-    return fma(y, e * fma(0.375, e, 0.5), y);               // y (1 + e/2 + 3 e^2 / 8)
-}
-__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0);                       // 1 - x y
-    return fma(y, fma(e, e, e), y);                         // y (1 + e + e^2)
-}
-__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
-
-// caller has already established 0 < r2 < rc2 with the exact test.  Branch-free: one rsqrt, one rcp.
-template <class R, int DIM, bool CONT, bool MOM>
-__device__ __forceinline__ void pair_body(const WcsphConst<R>& C, const IState<R, DIM>& I, R dx, R dy, R dz, R r2, R uj, R vj, R wj,
-                                          R rhoj, R mj, R por2j, Acc<R>& a) {
-    const R r = r2 * fast_rsqrt(r2);
-    const R t = (R)1 - r * I.half_inv_h;
-    const R gf = I.gfc * (t * t * t);
-    const R du = I.u - uj, dv = I.v - vj, dw = DIM == 3 ? I.w - wj : (R)0;
-    R vx = du * dx + dv * dy;
-    if (DIM == 3) vx += dw * dz;
-    const R mgf = mj * gf;
-    if (CONT) a.arho += mgf * vx;
-    if (MOM) {
-        // Pi = (beta mu - alpha c0) mu / rho_bar,  mu = h vx / (r2 + eta2),  rho_bar = (rho_i + rho_j)/2
-        const R rhos = I.rho + rhoj;
-        const R inv = fast_rcp((r2 + I.eta2) * rhos);
-        const R wv = I.h * vx * inv;                        // mu / (2 rho_bar)
-        const R mu = wv * rhos;
-        const R Pi = vx < (R)0 ? (C.beta * mu - C.alpha_c0) * (wv + wv) : (R)0;
-        const R c = -mgf * (I.por2 + por2j + Pi);
-        a.au += c * dx;
-        a.av += c * dy;
-        if (DIM == 3) a.aw += c * dz;
-    }
 }
 
 template <class R>
@@ -966,35 +896,23 @@ __global__ void __launch_bounds__(kThreads) k_wall_pressure(GridDev<R> g, WcsphC
     if (t >= pos[n]) return;                 // pos[n] = number of non-fluid particles (device-side count, no host sync)
     const int s = idx[t];
     const R xi = x[s], yi = y[s], zi = DIM == 3 ? z[s] : (R)0, hi = h[s];
-    const R pi = (R)3.14159265358979323846;
-    const R ad = DIM == 3 ? (R)(21.0 / 16.0) / (pi * hi * hi * hi) : (R)(7.0 / 4.0) / (pi * hi * hi);
+    const R ad = wendland_alpha<R, DIM>(hi);
     const R inv_h = (R)1 / hi;
     const R rc = mul_rn(C.kfac, hi);
     const R rc2 = mul_rn(rc, rc);
     const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
     const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
     const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
-    R S0 = 0, Sp = 0, Sx = 0, Sy = 0, Sz = 0;
+    WallSums<R> S{0, 0, 0, 0, 0};
     for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
         for (int j = b; j < e; ++j) {
             const R dx = xi - x[j], dy = yi - y[j], dz = DIM == 3 ? zi - z[j] : (R)0;
             const R r2 = dist2<DIM, R>(dx, dy, dz);
-            if (r2 < rc2 && r2 > (R)0 && tag[j] == 0) {
-                const R q = r2 * fast_rsqrt(r2) * inv_h;
-                const R tt = (R)1 - (R)0.5 * q;
-                const R t2 = tt * tt;
-                const R W = ad * (t2 * t2) * ((R)2 * q + (R)1);
-                S0 += W;
-                Sp += p[j] * W;
-                const R rW = rho[j] * W;
-                Sx += rW * dx; Sy += rW * dy;
-                if (DIM == 3) Sz += rW * dz;
-            }
+            if (r2 < rc2 && r2 > (R)0 && tag[j] == 0) wall_accumulate<R, DIM>(S, ad, inv_h, dx, dy, dz, r2, p[j], rho[j]);
         }
     });
-    R pv = (R)0;
-    if (S0 > (R)0) pv = (Sp + (C.g[0] * Sx + C.g[1] * Sy + C.g[2] * Sz)) / S0;
-    const R rw = C.rho0 * exp(log1p(max(pv / C.B, (R)-0.5)) / C.gamma);
+    R pv, rw;
+    wall_finish<R>(C, S, pv, rw);
     p[s] = pv;
     rho[s] = rw;
     por2[s] = pv / (rw * rw);
