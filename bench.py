@@ -204,8 +204,22 @@ def cpu_baseline(workload: str, budget_s: float = 20.0):
     reps = int(max(1, min(5, budget_s / max(t1, 1e-3) - 1)))
     t, cores = cpu_step_time(block, reps) if reps > 1 else (t1, cores)
     t = min(t, t1)
-    return {"value": block.n / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{desc}; oracle cell-list step (key+sort+permute+EOS+pair loop), best of {reps + 1}, {t * 1e3:.1f} ms/step"}
+    out = {"value": block.n / t, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{desc}; oracle cell-list step (key+sort+permute+EOS+pair loop), best of {reps + 1}, {t * 1e3:.1f} ms/step"}
+    if workload == "wcsph2d_20k":
+        # for configs[0] also the loop the reference's back-end actually emits (simple_cpu.rs:7-8): all pairs,
+        # one thread -- "reference loop semantics as written"
+        from oracle import oracle as orc
+        orc.set_num_threads(1)
+        try:
+            t0 = time.perf_counter()
+            orc.wcsph(block.dim, block.params, block.arrays)
+            ta = time.perf_counter() - t0
+        finally:
+            orc.set_num_threads(cores)
+        out["allpairs_literal"] = {"value": block.n / ta, "unit": UNIT, "cores": 1,
+                                   "sample": f"same block, literal for i {{ for j {{ bodies }} }} loop over all {block.n}^2 pairs, one evaluation, {ta * 1e3:.0f} ms"}
+    return out
 
 
 def run_reference(args, rank: int):
