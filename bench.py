@@ -37,6 +37,13 @@ B_ALG = {("wcsph", 3, "f64"): 350, ("wcsph", 3, "f32"): 202, ("wcsph", 2, "f64")
 B_FORCE = {("wcsph", 3, "f64"): 117, ("wcsph", 3, "f32"): 61, ("wcsph", 2, "f64"): 93, ("wcsph", 2, "f32"): 49}
 
 
+# algorithmic f64 flop per particle of the fused pair kernel (SURVEY.md 8d "FLOP figure for the co-bound"): ~8 flop per
+# candidate of the 27 (9) cell stencil + ~70 flop per in-range pair, at h = 1.2 dx, cutoff 2h, cell = cutoff:
+# 3D 373 candidates / 58 neighbours, 2D 52 / 18.  Peak: scripts/ubench/fp64_peak.cu, profiles/ubench_fp64_peak.txt.
+FLOP_FORCE = {3: 8 * 373 + 70 * 58, 2: 8 * 52 + 70 * 18}
+FP64_PEAK_TFLOPS = 36.5
+
+
 def dem_bytes(real: str, zbar: float):
     """(step, force-pass) algorithmic bytes per particle for 3D DEM with mean stored contacts zbar."""
     if real == "f64":
@@ -474,6 +481,11 @@ def main():
                     "stage_ms": {"nnps(keys+sort+table+permute" + ("+halo)" if world > 1 else ")"): t_nnps * 1e3, "eos": t_eos * 1e3, "pair_kernel": t_force * 1e3}}
         if coupled:
             roofline["stage_ms"]["contact_kernel"] = t_dem * 1e3
+        if args.real == "f64" and block.physics != "dem":
+            # the f64 pair kernel is bound on-chip, not by HBM: its FP64 fraction beside the HBM one
+            tf = FLOP_FORCE[block.dim] * n_local / t_force / 1e12
+            roofline["fp64_cobound"] = {"alg_flop_per_particle": FLOP_FORCE[block.dim], "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                        "frac": tf / FP64_PEAK_TFLOPS, "peak_source": "measured DFMA rate (profiles/ubench_fp64_peak.txt)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if coupled else "weak", "vs_baseline": None,
                 "dtype": args.real, "data": "synthetic",
