@@ -1,7 +1,10 @@
 """A/B of the fused pair kernel's phase 1 (torch-free, one process, both builds dlopen'ed side by side):
-  base   prestige_b200/libprestige_b200.so            float4 (x, y, z, index) per staged candidate, scalar FADD/FMUL/FFMA
-  p1soa  build_ab/libprestige_b200_p1soa.so (-DPST_P1_SOA)  SoA staging, packed FADD2/FMUL2/FFMA2 on two candidates at a time
-Checks that the results are BIT-IDENTICAL (f64 and f32, 3D, 2D and a coupled block) and prints ms per launch.
+  base   build_ab/libprestige_b200_aos.so  (make -C prestige_b200/csrc variant NAME=aos DEFS=-DPST_P1_AOS)
+         float4 (x, y, z, index) per staged candidate, scalar FADD/FMUL/FFMA -- the layout that shipped until this A/B
+  p1soa  prestige_b200/libprestige_b200.so  (the default build)  SoA staging, packed FADD2/FMUL2/FFMA2, two candidates at a time
+(When profiles/r1_exp_p1soa_ab.txt was recorded the roles were reversed: the default build was the float4 one and the SoA
+form was built with a define.)  Checks whether the results are bit-identical (f64 and f32, 3D, 2D and a coupled block)
+and prints ms per launch.
 Also times the stages of a coupled step with the dummy-particle wall pressure (default build).
 Output: gpurun_out/exp_p1soa.txt"""
 import os
@@ -15,7 +18,7 @@ import numpy as np  # noqa: E402
 import prestige_b200 as pb  # noqa: E402
 from prestige_b200 import _lib as L, synth  # noqa: E402
 
-LIBS = [("base", os.path.join(ROOT, "prestige_b200", "libprestige_b200.so")), ("p1soa", os.path.join(ROOT, "build_ab", "libprestige_b200_p1soa.so"))]
+LIBS = [("base", os.path.join(ROOT, "build_ab", "libprestige_b200_aos.so")), ("p1soa", os.path.join(ROOT, "prestige_b200", "libprestige_b200.so"))]
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 out = open(os.path.join(ROOT, "gpurun_out", "exp_p1soa.txt"), "w")
 
@@ -78,7 +81,7 @@ for name, *_ in cases:
         say(f"{name}: p1soa vs base {'bit-identical' if same else 'DIFFERENT, max rel %.2e' % worst}")
 
 # ---- stage times of a coupled step with the dummy-particle wall pressure (default build)
-use(LIBS[0][1])
+use(LIBS[1][1])
 c = synth.coupled_block_3d(125, 125, 128)
 c.params["boundary_model"] = 1.0
 with pb.context_for_block(c) as ctx:
