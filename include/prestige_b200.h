@@ -103,7 +103,8 @@ PST_API const char* pst_last_error(const pst_ctx* ctx);
 PST_API void* pst_stream(pst_ctx* ctx);
 PST_API pst_status pst_sync(pst_ctx* ctx);
 
-/* named scalar parameters: rho0 c0 gamma alpha beta kfac gx gy gz | dem_model kn gn kt gt mu dt Estar Gstar erest | rho_solid */
+/* named scalar parameters: rho0 c0 gamma alpha beta kfac gx gy gz | dem_model kn gn kt gt mu dt Estar Gstar erest | rho_solid |
+ * boundary_model (0: boundaries and solids are dynamic SPH particles; 1: dummy-particle wall pressure, see pst_apply) */
 PST_API pst_status pst_set_param(pst_ctx* ctx, const char* name, double value);
 PST_API pst_status pst_get_param(pst_ctx* ctx, const char* name, double* value);
 
