@@ -143,6 +143,7 @@ struct TileDims {
     static constexpr int RY = DIM == 3 ? BB + 2 : 1;               // runs along y
 };
 
+constexpr int kMaxTileG = 26;      // deepest tile: bounds the f32 error of the tile-local pre-filter (see launch_tiled)
 constexpr int kListsJcap = 1536;   // float4 slots staged per tile (24 KB): every KB not requested stays L1 for the phase-2 gathers (2048 -> 1536: -3 %)
 
 // UMASS: every particle has the mass A.m_uni (known from the host upload), so m[j] is not gathered.
@@ -730,6 +731,10 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
         else G = (int)std::floor(0.95 * NT / (D::NI * ppc));                        // one thread per particle
     }
     G = std::min(std::max(G, 1), std::max(1, nf));
+    // f32 pre-filter of f64 contexts: tile-local coordinates reach (G + 6) cells, where one f32 ulp is (G + 6) 2^-23 cells; the
+    // worst-case relative error of r2f is 2 sqrt(3) ulp / cutoff.  (G + 6) <= 32 keeps it below half of the 2^-15 margin
+    // (1.3e-5 < 1.5e-5; tests/test_prefilter_margin.py), so a true neighbour can never be filtered out.
+    G = std::min(G, kMaxTileG);
     G = std::min(G, (256 - 2 * D::NR - 2 * D::NI - 3) / D::NR - 3);   // boundary tables stay within 1 KB
     while (user_G <= 0 && G > 1 && 1.08 * D::NR * (G + 2) * ppc > jc_max) --G;   // the staged runs must fit (else: slow exact fallback)
     T.G = G;
