@@ -76,6 +76,9 @@ def test_library_exports_every_declared_symbol():
     declared = re.findall(r"PST_API\s+[\w\s\*]+?\b(pst_\w+)\s*\(", hdr)
     assert len(declared) >= 25
     assert sorted(declared) == sorted(_lib.SYMBOLS)
+    # the Rust FFI crate (source only, never compiled here) declares exactly the same entry points
+    rs = open(os.path.join(ROOT, "rust", "prestige_b200_sys", "src", "lib.rs")).read()
+    assert sorted(re.findall(r"pub fn (pst_\w+)", rs)) == sorted(declared)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for s in declared:
         assert hasattr(lib, s), f"{s} not exported"
