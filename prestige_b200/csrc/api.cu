@@ -458,12 +458,14 @@ void* pst_host_alloc(size_t bytes) {
 void pst_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 pst_status pst_build_neighbours(pst_ctx* ctx) {
+    PstRange range("pst_build_neighbours");
     if (!ctx) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     return pst_nnps_build(ctx);
 }
 
 pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
+    PstRange range("pst_apply");
     if (!ctx || !eq_names || n_eq <= 0) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     std::set<std::string> eqs;
@@ -516,6 +518,7 @@ pst_status pst_dump_pairs(pst_ctx* ctx, int mode, uint32_t* i, uint32_t* j, size
 }
 
 pst_status pst_integrate(pst_ctx* ctx, double dt) {
+    PstRange range("pst_integrate");
     if (!ctx) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     if (ctx->coupled) {
@@ -532,6 +535,7 @@ pst_status pst_integrate(pst_ctx* ctx, double dt) {
 }
 
 pst_status pst_step(pst_ctx* ctx, double dt, int n_steps) {
+    PstRange range("pst_step");
     if (!ctx || n_steps < 0) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     for (int k = 0; k < n_steps; ++k) {

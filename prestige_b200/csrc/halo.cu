@@ -424,6 +424,7 @@ static pst_status p2p_setup(pst_ctx* ctx, size_t bytes, int left, int right) {
 }
 
 extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
+    PstRange range("pst_halo_exchange");
     if (!ctx) return PST_EINVAL;
     if (!ctx->comm) return pst_fail(ctx, PST_ESTATE, "no communicator attached (pst_comm_init)");
     if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pst_halo_exchange");

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only (v3): a no-op unless a profiler injects itself
 #include <stdint.h>
 
 #include <map>
@@ -97,6 +98,14 @@ struct pst_ctx {
 };
 
 pst_status pst_fail(const pst_ctx* ctx, pst_status s, const char* fmt, ...);
+// NVTX range around a stage of the path (tracing): `nsys` timelines and `ncu --nvtx --nvtx-include "pst_apply/"`
+// can then select a stage by name.  Costs one predictable branch when no tool is attached.
+struct PstRange {
+    explicit PstRange(const char* name) { nvtxRangePushA(name); }
+    ~PstRange() { nvtxRangePop(); }
+    PstRange(const PstRange&) = delete;
+    PstRange& operator=(const PstRange&) = delete;
+};
 #define PST_CUDA(ctx, expr)                                                                       \
     do {                                                                                          \
         cudaError_t e__ = (expr);                                                                 \
