@@ -113,7 +113,10 @@ PST_API pst_status pst_get_param(pst_ctx* ctx, const char* name, double* value);
 PST_API pst_status pst_set_count(pst_ctx* ctx, uint64_t n);
 PST_API pst_status pst_get_count(pst_ctx* ctx, uint64_t* n_owned, uint64_t* n_ghost);
 PST_API pst_status pst_array_create(pst_ctx* ctx, const char* name, int dtype, uint32_t flags);
-/* device pointer (current buffer, cell order), element count per row, dtype, rows */
+/* device pointer (current buffer, cell order), element count per row, dtype, rows.  The pointer is for reading and for
+ * chaining device work; the library tracks one property of uploaded data -- whether all masses `m` are equal, which lets the
+ * fused pair kernel skip the m[j] gather -- so a caller that WRITES `m` through this pointer must say so with
+ * pst_set_option(ctx, "uniform_mass", 0) (or upload `m` again). */
 PST_API pst_status pst_array(pst_ctx* ctx, const char* name, void** dev_ptr, size_t* n, int* dtype, int* rows);
 /* host buffers hold rows * n elements, row-major, particle index = id */
 PST_API pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n);
