@@ -153,7 +153,10 @@ PST_API pst_status pst_integrate(pst_ctx* ctx, double dt);
 
 /* counters: n_cells max_cell_count launches pairs_tested contacts_total key_bits ... */
 PST_API pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value);
-/* select a kernel variant (A/B measurement): name "force_kernel" value 0 = per-particle gather, 1 = tiled */
+/* select a kernel variant (A/B measurement): name "force_kernel" value 0 = per-particle gather, 1 = warp per cell, 2 = tiled
+ * lists (default).  "uniform_mass" 0 = always gather m[j] (default 1: skip the gather when every uploaded mass is equal);
+ * "uniform_mass_global" 1 = multi-GPU: the caller guarantees that EVERY rank uploaded the same single mass value, so the
+ * skip also applies to ghosts and migrants (default 0: with a communicator m[j] is always gathered). */
 PST_API pst_status pst_set_option(pst_ctx* ctx, const char* name, int value);
 
 /* ---- multi-particle rigid bodies in a coupled context (no reference code) ---------------------

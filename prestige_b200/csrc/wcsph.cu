@@ -751,8 +751,11 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
         if (DIM == 3 && VARIANT == 2) return launch_tiled_k<R, 3, TA, TB, NT, 2, true, true, true>(ctx, T, smem);
         return pst_fail(ctx, PST_EINVAL, "coupled contexts need dim = 3 and force_kernel 0 or 2");
     }
-    // all masses equal (seen at upload; single rank, so no foreign ghosts): the fused kernel without the m[j] gather
-    const bool umass = VARIANT == 2 && ctx->m_uniform && !ctx->comm && pst_option(ctx, "uniform_mass", 1) != 0;
+    // all masses equal (seen at upload): the fused kernel without the m[j] gather.  With a communicator the ghosts and the
+    // migrants come from other ranks, whose uploads this rank has not seen: the caller vouches for them with the option
+    // "uniform_mass_global" = 1 (every rank uploaded the same single mass value; bench.py checks it with an all-reduce).
+    const bool umass = VARIANT == 2 && ctx->m_uniform && (!ctx->comm || pst_option(ctx, "uniform_mass_global", 0) != 0) &&
+                       pst_option(ctx, "uniform_mass", 1) != 0;
     if constexpr (VARIANT == 2) {
         if (cont && mom && umass) return launch_tiled_k<R, DIM, TA, TB, NT, 2, true, true, false, true>(ctx, T, smem);
     }

@@ -44,9 +44,11 @@ def halo_parity(out, rank, world, lr):
     whole = synth.wcsph_block_3d(60, 24, 20)
     res = {}
     ref = orc.wcsph(3, whole.params, whole.arrays, grid=orc.make_grid(3, whole.lo, whole.hi, whole.cell_size))
-    for variant in (2, 1, 0):
+    for variant in (2, "2g", 1, 0):                # "2g": the tiled kernel without the m[j] gather (every rank uploaded the same mass)
         ctx, own = _slab_context(whole, rank, world, lr)
-        ctx.set_option("force_kernel", variant)
+        ctx.set_option("force_kernel", 2 if variant == "2g" else variant)
+        if variant == "2g":
+            ctx.set_option("uniform_mass_global", 1)
         for rep in range(2):                     # second pass: identity re-sort + fresh halo
             ctx.build_neighbours()
             ctx.halo_exchange()
