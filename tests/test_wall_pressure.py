@@ -142,8 +142,7 @@ def test_wall_pressure_gpu_wcsph(real, key):
                     assert_close(ctx.download(k), ref[k], f"wall pressure {b.dim}D {k} eval {ev} {key}")
                 if ev == 0:                      # what the oracle sees on the second pass: the state the device now holds
                     ref = orc.wcsph(b.dim, b.params, dict(b.arrays, rho=ref["rho"]))
-        # golden fixture (f64, the small dam break)
-    if real == np.float64 and key == "linear":
+    if real == np.float64 and key == "linear":   # golden fixture (f64, the small dam break)
         z = np.load(os.path.join(GOLD, "wall2d_small.npz"))
         c = synth.wcsph_dambreak_2d(dx=0.05).shuffled()
         c.params["boundary_model"] = 1.0
