@@ -349,9 +349,8 @@ def main():
     if world > 1 and "m" in block.arrays:
         # the single-rank run skips the m[j] gather because every uploaded mass is equal; across ranks only the caller can know
         # that: tell the library when min == max over ALL ranks' particles, so every N times the same kernel
-        mm = torch.tensor([float(block.arrays["m"].min()), -float(block.arrays["m"].max())], device="cuda", dtype=torch.float64)
-        dist.all_reduce(mm, op=dist.ReduceOp.MIN)
-        if float(mm[0]) == -float(mm[1]):
+        from prestige_b200 import decomp
+        if decomp.uniform_across_ranks(block.arrays["m"], dist, device="cuda"):
             ctx.set_option("uniform_mass_global", 1)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     coupled = block.physics == "wcsph+dem"

@@ -53,3 +53,19 @@ def edge_layers(x: np.ndarray, lo: float, cell: float, n_layers: int):
 def ghost_capacity(ny_particles: int, nz_particles: int, cell: float, dx: float, slack: float = 1.5) -> int:
     """Upper estimate of one ghost layer's particle count for a lattice of spacing dx."""
     return int(math.ceil(cell / dx + 1) * ny_particles * nz_particles * slack)
+
+
+def uniform_across_ranks(values: np.ndarray, dist=None, device=None) -> bool:
+    """True iff every element of `values` on EVERY rank is the same number (one all-reduce of (min, -max)).
+    What the option "uniform_mass_global" asks the caller to vouch for: each rank's library only sees its own uploads,
+    ghosts and migrants come from the others.  `dist` = torch.distributed (initialised) or None for a single rank."""
+    if values.size == 0:
+        lo, hi = math.inf, -math.inf
+    else:
+        lo, hi = float(values.min()), float(values.max())
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+        t = torch.tensor([lo, -hi], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        lo, hi = float(t[0]), -float(t[1])
+    return lo == hi

@@ -82,7 +82,11 @@ def _worker(rank, world, port, q):
         err = max(np.abs(res[c][:n_own] - ref[c][own]).max() / np.abs(ref[c]).max() for c in ("au", "av", "aw", "arho"))
         tot = torch.tensor([n_own], dtype=torch.int64)
         dist.all_reduce(tot)
-        q.put((rank, ok_pairs, float(err), int(tot[0]), whole.n, len(fl), len(fr)))
+        # what bench.py asks before it lets every rank skip the m[j] gather: one mass value on ALL ranks
+        uni = (decomp.uniform_across_ranks(mine[:, 7], dist),                                   # the block's masses: all equal
+               decomp.uniform_across_ranks(mine[:, 7] * (1.0 + (rank == world - 1)), dist),     # one rank differs: every rank must see it
+               decomp.uniform_across_ranks(np.where(np.arange(n_own) == 0, 2.0, 1.0) if rank == 0 else np.ones(n_own), dist))
+        q.put((rank, ok_pairs, float(err), int(tot[0]), whole.n, len(fl), len(fr), uni))
     finally:
         dist.destroy_process_group()
 
@@ -99,7 +103,8 @@ def test_slab_decomposition_with_ghost_layers(world):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok_pairs, err, tot, n, nl, nr in res:
+    for rank, ok_pairs, err, tot, n, nl, nr, uni in res:
+        assert uni == (True, False, False), f"rank {rank}: cross-rank mass uniformity check {uni}"
         assert ok_pairs, f"rank {rank}: neighbour set of owned particles differs from the single-domain set"
         assert err < 1e-12, f"rank {rank}: {err:.3e}"
         assert tot == n, "every particle is owned by exactly one rank"
