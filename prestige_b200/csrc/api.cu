@@ -38,6 +38,54 @@ int pst_option(pst_ctx* ctx, const char* name, int dflt) {
 
 static size_t dtype_size(int dt) { return (dt == PST_F64) ? 8 : 4; }
 
+// Derive the cell grid from the configured box, the slab (when a communicator is attached: one ghost cell layer on each x
+// face) and the fast-axis subdivision `grid.sub`; (re)allocate the cell table for it.
+pst_status pst_grid_finalize(pst_ctx* ctx) {
+    PstGrid& g = ctx->grid;
+    const pst_config& cfg = ctx->cfg;
+    g.dim = cfg.dim;
+    g.cell = cfg.cell_size;
+    g.inv_cell = 1.0 / cfg.cell_size;
+    g.morton = cfg.key == PST_KEY_MORTON;
+    if (g.morton && g.sub != 1) return pst_fail(ctx, PST_EINVAL, "zsub > 1 needs linear keys");
+    double ncell_total = 1;
+    int nmax = 1;
+    for (int a = 0; a < 3; ++a) {
+        g.lo[a] = cfg.lo[a];
+        g.n[a] = 1;
+        if (a < cfg.dim) {
+            const double ext = cfg.hi[a] - cfg.lo[a];
+            if (!(ext >= 0)) return pst_fail(ctx, PST_EINVAL, "hi[%d] < lo[%d]", a, a);
+            g.n[a] = std::max(1, (int)std::ceil(ext / cfg.cell_size));
+        }
+    }
+    g.cx_lo = 0; g.cx_hi = g.n[0] - 1;
+    if (ctx->comm) {   // slab: whole number of cells along x (checked by pst_comm_init) + the two ghost layers
+        g.n[0] = (int)std::llround((cfg.hi[0] - cfg.lo[0]) / g.cell) + 2;
+        g.lo[0] = cfg.lo[0] - g.cell;
+        g.cx_lo = 1;
+        g.cx_hi = g.n[0] - 2;
+    }
+    g.nc_fast = g.n[cfg.dim - 1];
+    g.n[cfg.dim - 1] *= g.sub;
+    for (int a = 0; a < 3; ++a) { ncell_total *= g.n[a]; nmax = std::max(nmax, g.n[a]); }
+    if (g.morton) {
+        g.bits = 1;
+        while ((1 << g.bits) < nmax) ++g.bits;
+        if (g.bits > (cfg.dim == 3 ? 10 : 15)) return pst_fail(ctx, PST_EINVAL, "grid too large for Morton keys");
+        g.key_bits = g.bits * cfg.dim;
+        g.ncells = 1u << g.key_bits;
+    } else {
+        if (ncell_total >= 2147483647.0) return pst_fail(ctx, PST_EINVAL, "grid has too many cells (%g)", ncell_total);
+        g.ncells = (uint32_t)ncell_total;
+        g.key_bits = 1;
+        while ((1ull << g.key_bits) < g.ncells) ++g.key_bits;
+    }
+    ctx->nbrs_valid = false;
+    ctx->params.erase("_ppc");
+    return pst_nnps_alloc_table(ctx);
+}
+
 // "m" arrives from the host only (pst_upload / pst_upload_async): remember whether all masses are equal, so the fused
 // pair kernel can use the value instead of gathering m[j] for every pair (one of its nine 8-byte gathers).
 static void note_mass_upload(pst_ctx* ctx, const PstArray* a, const void* host, size_t n) {
@@ -118,44 +166,13 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
         pst_fail(ctx, PST_ECUDA, "cudaStreamCreate failed");
         return bail(PST_ECUDA);
     }
-    // grid
-    PstGrid& g = ctx->grid;
-    g.dim = cfg->dim;
-    g.cell = cfg->cell_size;
-    g.inv_cell = 1.0 / cfg->cell_size;
-    g.morton = cfg->key == PST_KEY_MORTON;
-    double ncell_total = 1;
-    int nmax = 1;
-    for (int a = 0; a < 3; ++a) {
-        g.lo[a] = cfg->lo[a];
-        g.n[a] = 1;
-        if (a < cfg->dim) {
-            const double ext = cfg->hi[a] - cfg->lo[a];
-            if (!(ext >= 0)) { pst_fail(ctx, PST_EINVAL, "hi[%d] < lo[%d]", a, a); return bail(PST_EINVAL); }
-            g.n[a] = std::max(1, (int)std::ceil(ext / cfg->cell_size));
-        }
-        ncell_total *= g.n[a];
-        nmax = std::max(nmax, g.n[a]);
-    }
-    g.cx_lo = 0; g.cx_hi = g.n[0] - 1;
-    if (g.morton) {
-        g.bits = 1;
-        while ((1 << g.bits) < nmax) ++g.bits;
-        if (g.bits > (cfg->dim == 3 ? 10 : 15)) { pst_fail(ctx, PST_EINVAL, "grid too large for Morton keys"); return bail(PST_EINVAL); }
-        g.key_bits = g.bits * cfg->dim;
-        g.ncells = 1u << g.key_bits;
-    } else {
-        if (ncell_total >= 2147483647.0) { pst_fail(ctx, PST_EINVAL, "grid has too many cells (%g)", ncell_total); return bail(PST_EINVAL); }
-        g.ncells = (uint32_t)ncell_total;
-        g.key_bits = 1;
-        while ((1ull << g.key_bits) < g.ncells) ++g.key_bits;
-    }
     // default parameters
     ctx->params = {{"rho0", 1000.0}, {"c0", 10.0}, {"gamma", 7.0}, {"alpha", 0.1}, {"beta", 0.0}, {"kfac", 2.0},
                    {"gx", 0.0}, {"gy", 0.0}, {"gz", 0.0}, {"dem_model", 0.0}, {"kn", 1e5}, {"gn", 0.0}, {"kt", 2e4},
                    {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}, {"rho_solid", 2500.0},
                    {"boundary_model", 0.0}};   // 1: dummy-particle wall pressure in pst_step, wall density slaved
-    pst_status s = PST_OK;
+    pst_status s = pst_grid_finalize(ctx);   // grid + cell table
+    if (s != PST_OK) return bail(s);
     auto mk = [&](const char* name, int dt, uint32_t fl, int rows = 1) { if (s == PST_OK) s = array_create(ctx, name, dt, fl, rows); };
     const uint32_t P = PST_ARRAY_PERSISTENT, O = PST_ARRAY_OUTPUT;
     mk("id", PST_U32, P);
@@ -337,8 +354,42 @@ pst_status pst_get_param(pst_ctx* ctx, const char* name, double* value) {
 }
 pst_status pst_set_option(pst_ctx* ctx, const char* name, int value) {
     if (!ctx || !name) return PST_EINVAL;
-    ctx->options[name] = value;
-    return PST_OK;
+    // every option the kernels read, with its valid range: a typo or an out-of-range value is an error, never silently ignored
+    static const struct { const char* name; int lo, hi; } known[] = {
+        {"force_kernel", 0, 3},          // WCSPH pair kernel: 0 gather | 1 warp per cell | 2 tiled lists | 3 tiled z-runs + bit masks
+        {"dem_kernel", 0, 2},
+        {"sort_impl", 0, 1},             // 0 library radix sort + bounds kernel (A/B) | 1 counting sort (default)
+        {"halo_impl", 0, 2},             // 0 per-array NCCL | 1 packed NCCL | 2 peer memory (default)
+        {"uniform_mass", 0, 1},
+        {"uniform_mass_global", 0, 1},
+        {"tile_g", 0, 64},               // 0 = from the measured cell occupancy
+        {"tile_lcap", 4, 256},
+        {"tile_jcap", 0, 1 << 20},
+        {"tile_ta", 2, 3},
+        {"zsub", 1, 8},                  // fast-axis subdivision of the cell grid: 1, 2, 4 or 8
+        {"tile_words", 4, 64},
+        {"rec_impl", 0, 1},
+        {"graph", 0, 1},
+    };
+    const std::string nm = name;
+    for (const auto& k : known) {
+        if (nm != k.name) continue;
+        if (value < k.lo || value > k.hi) return pst_fail(ctx, PST_EINVAL, "option '%s' = %d is outside [%d, %d]", name, value, k.lo, k.hi);
+        if (nm == "zsub") {
+            if (value & (value - 1)) return pst_fail(ctx, PST_EINVAL, "option 'zsub' must be 1, 2, 4 or 8");
+            if (ctx->comm) return pst_fail(ctx, PST_ESTATE, "set 'zsub' before pst_comm_init (the halo windows are sized by the cell layer)");
+            if (value != ctx->grid.sub) {
+                PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+                const int old = ctx->grid.sub;
+                ctx->grid.sub = value;
+                const pst_status st = pst_grid_finalize(ctx);
+                if (st != PST_OK) { ctx->grid.sub = old; pst_grid_finalize(ctx); return st; }
+            }
+        }
+        ctx->options[nm] = value;
+        return PST_OK;
+    }
+    return pst_fail(ctx, PST_EINVAL, "unknown option '%s'", name);
 }
 
 pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {

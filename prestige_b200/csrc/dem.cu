@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(kThreads) k_dem_forces_generic(GridDev<R> g, D
     const R owx = mul_rn(ri, A.wx[s]), owy = mul_rn(ri, A.wy[s]), owz = mul_rn(ri, A.wz[s]);   // R_i w_i
     const int hrow = A.hperm ? (int)A.hperm[s] : s;
     const int nold = A.hn_in[hrow];
-    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
-    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1);
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv[0], g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = cell_coord<R>(zi, g.lo[2], g.inv[2], 0, g.n[2] - 1);
     R fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
     int cnt = 0;
     for_each_run<3, MORTON>(g, A.cell_start, cx, cy, cz, [&](int b, int e) {
@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(kThreads, 6) k_dem_forces(GridDev<R> g, DemCon
     }
     const R xi = A.x[s], yi = A.y[s], zi = A.z[s];
     const R ri = A.rad[s];
-    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
-    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1);
-    const int zl = max(cz - 1, 0), zh = min(cz + 1, g.n[2] - 1);
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv[0], g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = cell_coord<R>(zi, g.lo[2], g.inv[2], 0, g.n[2] - 1);
+    const int zl = max(cz - g.sub, 0), zh = min(cz + g.sub, g.n[2] - 1);
     int rb[9], re[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {

@@ -262,36 +262,24 @@ extern "C" pst_status pst_comm_init(pst_ctx* ctx, const void* id_bytes, int rank
     const double cells = ext / g.cell;
     if (std::fabs(cells - std::round(cells)) > 1e-6 * std::max(1.0, cells))
         return pst_fail(ctx, PST_EINVAL, "slab x extent %.17g is not a whole number of cells (%.17g)", ext, g.cell);
-    g.n[0] = (int)std::llround(cells) + 2;
-    g.lo[0] = ctx->cfg.lo[0] - g.cell;
-    g.cx_lo = 1;
-    g.cx_hi = g.n[0] - 2;
-    const double total = (double)g.n[0] * g.n[1] * g.n[2];
-    if (total >= 2147483647.0) return pst_fail(ctx, PST_EINVAL, "grid has too many cells");
-    g.ncells = (uint32_t)total;
-    g.key_bits = 1;
-    while ((1ull << g.key_bits) < g.ncells) ++g.key_bits;
-    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    PST_CUDA(ctx, cudaFree(ctx->cell_start));
-    ctx->cell_start = nullptr;
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)g.ncells + 4) * 4));
-    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)g.ncells + 4) * 4, ctx->stream));
-    PST_CUDA(ctx, cudaFree(ctx->scan_sums));
-    ctx->scan_sums = nullptr;
-    ctx->scan_sums_cap = ((size_t)g.ncells + 4) / 4096 + 2;
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     PstComm* c = new PstComm();
     c->rank = rank; c->nranks = n_ranks;
+    ctx->comm = c;                                   // the grid of a slab has the two ghost layers
+    const pst_status gs = pst_grid_finalize(ctx);
+    ctx->comm = nullptr;
+    if (gs != PST_OK) { delete c; pst_grid_finalize(ctx); return gs; }
     const size_t layer = (size_t)g.n[1] * g.n[2] + 1;
     if (cudaMalloc((void**)&c->d_counts, 16 * 4) != cudaSuccess || cudaMalloc((void**)&c->d_tab_l, layer * 4) != cudaSuccess ||
         cudaMalloc((void**)&c->d_tab_r, layer * 4) != cudaSuccess || cudaHostAlloc((void**)&c->h_counts, 16 * 4, cudaHostAllocDefault) != cudaSuccess) {
+        cudaFree(c->d_counts); cudaFree(c->d_tab_l); cudaFree(c->d_tab_r);
         delete c;
+        pst_grid_finalize(ctx);
         return pst_fail(ctx, PST_ENOMEM, "halo buffers");
     }
     ncclUniqueId id;
     std::memcpy(&id, id_bytes, sizeof id);
     ncclResult_t r = api->CommInitRank(&c->comm, n_ranks, id, rank);
-    if (r != 0) { delete c; return pst_fail(ctx, PST_ENCCL, "ncclCommInitRank: %s", api->GetErrorString(r)); }
+    if (r != 0) { delete c; pst_grid_finalize(ctx); return pst_fail(ctx, PST_ENCCL, "ncclCommInitRank: %s", api->GetErrorString(r)); }
     ctx->comm = c;
     ctx->nbrs_valid = false;
     return PST_OK;

@@ -31,10 +31,10 @@ __global__ void __launch_bounds__(kThreads) k_keys(GridDev<R> g, int n, const R*
                                                    uint32_t* __restrict__ vals, uint32_t ncells, int mig_l, int mig_r) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const int cxu = (int)floor((x[s] - g.lo[0]) * g.inv_cell);
+    const int cxu = (int)floor((x[s] - g.lo[0]) * g.inv[0]);
     const int cx = min(max(cxu, g.cx_lo), g.cx_hi);
-    const int cy = cell_coord<R>(y[s], g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    const int cy = cell_coord<R>(y[s], g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv[2], 0, g.n[2] - 1) : 0;
     uint32_t key = cell_key<DIM, MORTON>(g, cx, cy, cz);
     if (mig_l && cxu < g.cx_lo) key = ncells;
     else if (mig_r && cxu > g.cx_hi) key = ncells + 1u;
@@ -75,10 +75,10 @@ __global__ void __launch_bounds__(kThreads) k_keys_count(GridDev<R> g, int n, co
                                                          int32_t* __restrict__ count, uint32_t ncells, int mig_l, int mig_r) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const int cxu = (int)floor((x[s] - g.lo[0]) * g.inv_cell);
+    const int cxu = (int)floor((x[s] - g.lo[0]) * g.inv[0]);
     const int cx = min(max(cxu, g.cx_lo), g.cx_hi);
-    const int cy = cell_coord<R>(y[s], g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    const int cy = cell_coord<R>(y[s], g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(z[s], g.lo[2], g.inv[2], 0, g.n[2] - 1) : 0;
     uint32_t key = cell_key<DIM, MORTON>(g, cx, cy, cz);
     if (mig_l && cxu < g.cx_lo) key = ncells;
     else if (mig_r && cxu > g.cx_hi) key = ncells + 1u;
@@ -89,15 +89,18 @@ __global__ void __launch_bounds__(kThreads) k_keys_count(GridDev<R> g, int n, co
 constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
 
 // block-level exclusive scan of one tile, in place; tile total -> sums[blockIdx.x]; also counts non-empty cells
+// (`sub`: the fast axis of the grid is subdivided; `sub` consecutive entries -- aligned, since every column holds a multiple
+// of `sub` fine cells -- form one coarse cell, and it is the coarse cells that are counted)
 __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(int m, int32_t* __restrict__ a, int32_t* __restrict__ sums,
-                                                             unsigned long long* __restrict__ counters) {
+                                                             unsigned long long* __restrict__ counters, int sub) {
     __shared__ int warp_tot[kScanThreads / 32];
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    int v[kScanItems], t = 0, occ = 0;
+    int v[kScanItems], t = 0, occ = 0, grp = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         v[k] = base + k < m ? a[base + k] : 0;
-        occ += v[k] != 0;
+        grp += v[k];
+        if (((k + 1) & (sub - 1)) == 0) { occ += grp != 0; grp = 0; }
         const int x = v[k]; v[k] = t; t += x;          // exclusive within the thread
     }
     int incl = t;
@@ -277,9 +280,9 @@ __global__ void __launch_bounds__(kThreads) k_dump_pairs(GridDev<R> g, int n, in
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const R xi = x[s], yi = y[s], zi = DIM == 3 ? z[s] : (R)0, si = sz[s];
-    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
-    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv[0], g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv[2], 0, g.n[2] - 1) : 0;
     const uint32_t idi = id[s];
     const int ti = tag ? tag[s] : 0;
     if (tag && mode == 1 && ti != 2) return;
@@ -354,8 +357,6 @@ pst_status pst_nnps_alloc(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->keys_out, cap * 4));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->vals_in, cap * 4));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->vals_out, cap * 4));
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, ((size_t)ctx->grid.ncells + 4) * 4));
-    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)ctx->grid.ncells + 4) * 4, ctx->stream));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->stage, cap * 8));
     PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_flags, 8 * sizeof(int32_t)));
     PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
@@ -364,12 +365,23 @@ pst_status pst_nnps_alloc(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 8 * sizeof(int32_t), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     PST_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stats, cudaEventDisableTiming));
-    ctx->scan_sums_cap = ((size_t)ctx->grid.ncells + 4) / kScanTile + 2;
-    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     ctx->sort_tmp_bytes = 0;
     PST_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, ctx->keys_in, ctx->keys_out, ctx->vals_in,
                                                   ctx->vals_out, (int)cap, 0, 32, ctx->stream));
     PST_CUDA(ctx, cudaMalloc(&ctx->sort_tmp, ctx->sort_tmp_bytes));
+    return PST_OK;
+}
+
+// cell table (ncells + 1 entries, + the two migration sentinels) and the tile sums of its scan, for the current grid
+pst_status pst_nnps_alloc_table(pst_ctx* ctx) {
+    if (ctx->stream) PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->cell_start); ctx->cell_start = nullptr;
+    cudaFree(ctx->scan_sums); ctx->scan_sums = nullptr;
+    const size_t entries = (size_t)ctx->grid.ncells + 4;
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->cell_start, entries * 4));
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, entries * 4, ctx->stream));
+    ctx->scan_sums_cap = entries / kScanTile + 2;
+    PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     return PST_OK;
 }
 
@@ -403,7 +415,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
         PST_CUDA(ctx, cudaMemsetAsync(ctx->cell_start, 0, ((size_t)nkeys + 2) * 4, ctx->stream));
         if (n > 0) PST_TRY(PST_DISPATCH(ctx, launch_keys_count, ctx, mig_l, mig_r));
         const int nb = (m + kScanTile - 1) / kScanTile;
-        PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums, ctx->d_counters);
+        PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums, ctx->d_counters, ctx->grid.sub);
         PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
         PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums);
         if (n > 0) {
@@ -481,7 +493,7 @@ pst_status pst_scan_exclusive(pst_ctx* ctx, int32_t* a, int m) {
         ctx->scan_sums_cap = (size_t)nb + 2;
         PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     }
-    PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, a, ctx->scan_sums, (unsigned long long*)nullptr);
+    PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, a, ctx->scan_sums, (unsigned long long*)nullptr, 1);
     PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
     PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, a, ctx->scan_sums);
     return PST_OK;

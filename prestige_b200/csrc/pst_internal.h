@@ -30,6 +30,10 @@ struct PstGrid {
     int n[3] = {1, 1, 1};    // cells per axis (x includes the two ghost layers when a communicator is attached)
     double lo[3] = {0, 0, 0};
     double cell = 1, inv_cell = 1;
+    int sub = 1;             // linear keys: the FAST axis (z in 3D, y in 2D) is cut `sub` times finer than `cell`, so the fine
+                             // cells of a column stay one contiguous run and a particle's stencil along it is +-sub fine cells
+                             // (option "zsub"); n[fast] counts FINE cells, nc_fast the coarse ones
+    int nc_fast = 1;
     int morton = 0;
     int bits = 0;            // morton: bits per axis
     int key_bits = 1;        // radix-sort end bit
@@ -145,6 +149,8 @@ int pst_option(pst_ctx* ctx, const char* name, int dflt = 0);
 // stage implementations (one per .cu)
 pst_status pst_nnps_build(pst_ctx* ctx);                                 // nnps.cu
 pst_status pst_nnps_alloc(pst_ctx* ctx);
+pst_status pst_nnps_alloc_table(pst_ctx* ctx);                           // (re)allocate the cell table for the current grid
+pst_status pst_grid_finalize(pst_ctx* ctx);                              // api.cu: box + slab + zsub -> grid, then the table
 pst_status pst_scan_exclusive(pst_ctx* ctx, int32_t* a, int m);        // in place, m entries (nnps.cu)
 pst_status pst_sort_pairs_u32(pst_ctx* ctx, int n);                       // keys_in/vals_in -> keys_out/vals_out, stable (nnps.cu)
 pst_status pst_resolve_history(pst_ctx* ctx);   // run the deferred k_remap_history, if any
@@ -189,8 +195,10 @@ __device__ __forceinline__ R dist2(R dx, R dy, R dz) {
 template <class R>
 struct GridDev {
     R lo[3];
-    R inv_cell, cell;
+    R inv[3];                // 1 / cell edge per axis (the fast axis of a subdivided grid is finer)
+    R cell;
     int n[3];
+    int sub;                 // stencil half-width along the fast axis, in (fine) cells
     int cx_lo, cx_hi;
     int bits;
 };
@@ -237,7 +245,7 @@ __device__ __forceinline__ void for_each_run(const GridDev<R>& g, const int32_t*
     if (DIM == 3) {
         for (int ax = max(cx - 1, 0); ax <= min(cx + 1, g.n[0] - 1); ++ax)
             for (int ay = max(cy - 1, 0); ay <= min(cy + 1, g.n[1] - 1); ++ay) {
-                const int zl = max(cz - 1, 0), zh = min(cz + 1, g.n[2] - 1);
+                const int zl = max(cz - (MORTON ? 1 : g.sub), 0), zh = min(cz + (MORTON ? 1 : g.sub), g.n[2] - 1);
                 if (MORTON) {
                     for (int az = zl; az <= zh; ++az) {
                         const uint32_t k = cell_key<3, true>(g, ax, ay, az);
@@ -249,7 +257,7 @@ __device__ __forceinline__ void for_each_run(const GridDev<R>& g, const int32_t*
             }
     } else {
         for (int ax = max(cx - 1, 0); ax <= min(cx + 1, g.n[0] - 1); ++ax) {
-            const int yl = max(cy - 1, 0), yh = min(cy + 1, g.n[1] - 1);
+            const int yl = max(cy - (MORTON ? 1 : g.sub), 0), yh = min(cy + (MORTON ? 1 : g.sub), g.n[1] - 1);
             if (MORTON) {
                 for (int ay = yl; ay <= yh; ++ay) {
                     const uint32_t k = cell_key<2, true>(g, ax, ay, 0);
@@ -266,7 +274,9 @@ template <class R>
 inline GridDev<R> make_grid_dev(const PstGrid& g) {
     GridDev<R> d;
     for (int a = 0; a < 3; ++a) { d.lo[a] = (R)g.lo[a]; d.n[a] = g.n[a]; }
-    d.inv_cell = (R)g.inv_cell; d.cell = (R)g.cell;
+    d.cell = (R)g.cell;
+    d.sub = g.sub;
+    for (int a = 0; a < 3; ++a) d.inv[a] = (R)(a == g.dim - 1 ? g.inv_cell * g.sub : g.inv_cell);
     d.cx_lo = g.cx_lo; d.cx_hi = g.cx_hi;
     d.bits = g.bits;
     return d;

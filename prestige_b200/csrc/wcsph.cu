@@ -89,9 +89,9 @@ template <class R, int DIM, bool MORTON, bool CONT, bool MOM, bool COUPLED = fal
 __device__ __forceinline__ void gather_one(const GridDev<R>& g, const WcsphConst<R>& C, const ForceArgs<R>& A, int s) {
     IState<R, DIM> I;
     load_i<R, DIM>(I, C, A.x[s], A.y[s], DIM == 3 ? A.z[s] : (R)0, A.u[s], A.v[s], DIM == 3 ? A.w[s] : (R)0, A.rho[s], A.por2[s], A.h[s]);
-    const int cx = cell_coord<R>(I.x, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
-    const int cy = cell_coord<R>(I.y, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    const int cx = cell_coord<R>(I.x, g.lo[0], g.inv[0], g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(I.y, g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv[2], 0, g.n[2] - 1) : 0;
     Acc<R> a{0, 0, 0, 0};
     const bool fluid_i = !COUPLED || A.m[s] > (R)0;
     for_each_run<DIM, MORTON>(g, A.cell_start, cx, cy, cz, [&](int b, int e) {
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_tiled(GridDev<R> g, WcsphConst<
             lx = c / BB; ly = c - lx * BB;
             load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
                            A.por2[gi], A.h[gi]);
-            const int cf = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : cell_coord<R>(I.y, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
+            const int cf = DIM == 3 ? cell_coord<R>(I.z, g.lo[2], g.inv[2], 0, g.n[2] - 1) : cell_coord<R>(I.y, g.lo[1], g.inv[1], 0, g.n[1] - 1);
             lf = cf - f0;   // 0 .. G-1
             xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
             if (LOCAL) rc2f = far ? __int_as_float(0x7f800000) : __double2float_ru((double)I.rc2 * (1.0 + 1.0 / 32768.0));
@@ -764,10 +764,15 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
     return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, false, true>(ctx, T, smem);
 }
 
+#include "wcsph_zrun.cuh"   // variant 3: tiles + fine z-runs + bit masks
+
 template <class R, int DIM, bool MORTON>
 pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
-    int variant = pst_option(ctx, "force_kernel", 2);   // 2 = thread-per-particle lists (fastest measured), 1 = warp-per-cell, 0 = gather
+    int variant = pst_option(ctx, "force_kernel", 2);   // 3 = tiled z-runs + bit masks, 2 = thread-per-particle lists, 1 = warp-per-cell, 0 = gather
     if (ctx->coupled && variant == 1) variant = 2;      // the warp-per-cell kernel has no coupled form
+    if (variant == 3 && !MORTON) return launch_zrun<R, DIM>(ctx, cont, mom);
+    if ((variant == 1 || variant == 2) && !MORTON && ctx->grid.sub != 1)
+        return pst_fail(ctx, PST_EINVAL, "force_kernel %d needs zsub = 1 (its tiles are cut in whole cells)", variant);
     if (variant == 1 && !MORTON) return launch_tiled<R, DIM, 1, 2>(ctx, cont, mom);
     if (variant == 2 && !MORTON) return pst_option(ctx, "tile_ta", 2) == 3 ? launch_tiled<R, DIM, 2, 3>(ctx, cont, mom) : launch_tiled<R, DIM, 2, 2>(ctx, cont, mom);
     return launch_gather<R, DIM, MORTON>(ctx, cont, mom);
@@ -908,9 +913,9 @@ __global__ void __launch_bounds__(kThreads) k_wall_pressure(GridDev<R> g, WcsphC
     const R inv_h = (R)1 / hi;
     const R rc = mul_rn(C.kfac, hi);
     const R rc2 = mul_rn(rc, rc);
-    const int cx = cell_coord<R>(xi, g.lo[0], g.inv_cell, g.cx_lo, g.cx_hi);
-    const int cy = cell_coord<R>(yi, g.lo[1], g.inv_cell, 0, g.n[1] - 1);
-    const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv_cell, 0, g.n[2] - 1) : 0;
+    const int cx = cell_coord<R>(xi, g.lo[0], g.inv[0], g.cx_lo, g.cx_hi);
+    const int cy = cell_coord<R>(yi, g.lo[1], g.inv[1], 0, g.n[1] - 1);
+    const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv[2], 0, g.n[2] - 1) : 0;
     WallSums<R> S{0, 0, 0, 0, 0};
     for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
         for (int j = b; j < e; ++j) {
