@@ -97,13 +97,21 @@ class Context:
         self._ck(self._lib.pst_array_create(self._h, name.encode(), dt, L.PST_ARRAY_PERSISTENT if persistent else L.PST_ARRAY_OUTPUT))
 
     def array_info(self, name: str):
+        """(None, n, dtype, rows): shape only.  The device pointer is NOT requested: handing it out tells the library the
+        caller may write through it (packed copies and the uniform-mass decision are then refreshed); see array_ptr."""
+        n, dt, rows = C.c_size_t(), C.c_int(), C.c_int()
+        self._ck(self._lib.pst_array(self._h, name.encode(), None, C.byref(n), C.byref(dt), C.byref(rows)))
+        return None, n.value, _NP[dt.value], rows.value
+
+    def array_ptr(self, name: str) -> int:
+        """Device pointer of the current buffer (cell order), for chaining device work."""
         p, n, dt, rows = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
         self._ck(self._lib.pst_array(self._h, name.encode(), C.byref(p), C.byref(n), C.byref(dt), C.byref(rows)))
-        return p.value, n.value, _NP[dt.value], rows.value
+        return p.value
 
     def has_array(self, name: str) -> bool:
-        p, n, dt, rows = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
-        return self._lib.pst_array(self._h, name.encode(), C.byref(p), C.byref(n), C.byref(dt), C.byref(rows)) == L.PST_OK
+        n, dt, rows = C.c_size_t(), C.c_int(), C.c_int()
+        return self._lib.pst_array(self._h, name.encode(), None, C.byref(n), C.byref(dt), C.byref(rows)) == L.PST_OK
 
     def upload(self, name: str, host: np.ndarray):
         _, _, dt, rows = self.array_info(name)

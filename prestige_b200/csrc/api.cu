@@ -86,23 +86,9 @@ pst_status pst_grid_finalize(pst_ctx* ctx) {
     return pst_nnps_alloc_table(ctx);
 }
 
-// "m" arrives from the host only (pst_upload / pst_upload_async): remember whether all masses are equal, so the fused
-// pair kernel can use the value instead of gathering m[j] for every pair (one of its nine 8-byte gathers).
-static void note_mass_upload(pst_ctx* ctx, const PstArray* a, const void* host, size_t n) {
-    if (a->name != "m") return;
-    ctx->m_uniform = false;
-    if (n == 0) return;
-    bool same = true;
-    if (a->dtype == PST_F64) {
-        const double* h = (const double*)host;
-        for (size_t k = 1; k < n && same; ++k) same = h[k] == h[0];
-        ctx->m_value = h[0];
-    } else {
-        const float* h = (const float*)host;
-        for (size_t k = 1; k < n && same; ++k) same = h[k] == h[0];
-        ctx->m_value = (double)h[0];
-    }
-    ctx->m_uniform = same;
+// m and h decide which pair kernel runs (uniform values become constants); whoever may have changed them marks the check stale
+static void note_uniform_dirty(pst_ctx* ctx, const PstArray* a) {
+    if (a->name == "m" || a->name == "h") ctx->uni_dirty = true;
 }
 
 static pst_status array_create(pst_ctx* ctx, const char* name, int dtype, uint32_t flags, int rows) {
@@ -213,11 +199,12 @@ void pst_destroy(pst_ctx* ctx) {
     pst_comm_destroy(ctx);
     for (auto& a : ctx->arrays) { cudaFree(a.buf[0]); if (a.buf[1]) cudaFree(a.buf[1]); }
     cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
-    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->wp_pos); cudaFree(ctx->wp_idx); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
+    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->wp_pos); cudaFree(ctx->wp_idx); cudaFree(ctx->rec); cudaFree(ctx->d_uni); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
     cudaFree(ctx->d_counters);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_uni) cudaFreeHost(ctx->h_uni);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h2d_stream) { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamDestroy(ctx->h2d_stream); }
     if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
@@ -300,7 +287,7 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
     if (!ctx->ordered || ctx->comm || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / distributed mode / history rows: plain path
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    note_mass_upload(ctx, a, host, n);
+    note_uniform_dirty(ctx, a);
     int k = 0;
     PST_TRY(ring_acquire(ctx, ctx->h2d_stream, true, &k));
     PST_CUDA(ctx, cudaMemcpyAsync(ctx->ring[k], host, n * a->esize, cudaMemcpyHostToDevice, ctx->h2d_stream));
@@ -314,6 +301,7 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     PST_CUDA(ctx, cudaEventRecord(ctx->ring_free[k], ctx->stream));
     if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
     if (a->name == "rho" || a->name == "m" || a->name == "tag") ctx->eos_valid = false;
+    ctx->state_epoch++;
     return PST_OK;
 }
 
@@ -343,6 +331,7 @@ pst_status pst_set_param(pst_ctx* ctx, const char* name, double value) {
     if (!ctx->params.count(name)) return pst_fail(ctx, PST_EINVAL, "unknown parameter '%s'", name);
     ctx->params[name] = value;
     ctx->eos_valid = false;
+    ctx->state_epoch++;
     return PST_OK;
 }
 pst_status pst_get_param(pst_ctx* ctx, const char* name, double* value) {
@@ -369,6 +358,9 @@ pst_status pst_set_option(pst_ctx* ctx, const char* name, int value) {
         {"zsub", 1, 8},                  // fast-axis subdivision of the cell grid: 1, 2, 4 or 8
         {"tile_words", 4, 64},
         {"rec_impl", 0, 1},
+        {"tile_dbg", 0, 9},
+        {"tile_gf", 0, 256},
+        {"tile_jc", 0, 1},              // timing ablations of the variant-3 kernel (WRONG results): 1 no gathers, 2 no pair body, 3 scan only
         {"graph", 0, 1},
     };
     const std::string nm = name;
@@ -403,8 +395,10 @@ pst_status pst_set_count(pst_ctx* ctx, uint64_t n) {
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;
     ctx->hist_lag = false;
+    ctx->state_epoch++;
     ctx->bodies_ready = false;       // a new particle set: pst_bodies_setup again
-    ctx->m_uniform = false;          // ... and its masses are not known yet
+    ctx->m_uniform = ctx->h_uniform = false;   // ... and its masses and smoothing lengths are not known yet
+    ctx->uni_dirty = true;
     PST_TRY(pst_iota_ids(ctx));
     if (PstArray* hn = pst_find(ctx, "hist_n")) {
         const size_t stride = ctx->capacity + 2 * ctx->ghost_cap;
@@ -433,7 +427,7 @@ pst_status pst_array(pst_ctx* ctx, const char* name, void** dev_ptr, size_t* n, 
     if (!ctx || !name) return PST_EINVAL;
     PstArray* a = pst_find(ctx, name);
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
-    if (dev_ptr) *dev_ptr = pst_ptr<char>(ctx, a);
+    if (dev_ptr) { *dev_ptr = pst_ptr<char>(ctx, a); ctx->state_epoch++; note_uniform_dirty(ctx, a); }   // the caller may write through it
     if (n) *n = ctx->n;
     if (dtype) *dtype = a->dtype;
     if (rows) *rows = a->rows;
@@ -446,7 +440,7 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles (pst_set_count first)", name, n, (unsigned long long)ctx->n);
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    note_mass_upload(ctx, a, host, n);
+    note_uniform_dirty(ctx, a);
     if (a->name.rfind("hist_", 0) == 0) PST_TRY(pst_resolve_history(ctx));
     if (a->name == "id") {
         // Restoring a checkpoint in DEVICE order: right after pst_set_count (identity order) the caller may declare
@@ -480,6 +474,7 @@ pst_status pst_upload(pst_ctx* ctx, const char* name, const void* host, size_t n
     }
     if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
     if (a->name == "rho" || a->name == "m" || a->name == "tag") ctx->eos_valid = false;
+    ctx->state_epoch++;
     return PST_OK;
 }
 
@@ -582,6 +577,7 @@ pst_status pst_integrate(pst_ctx* ctx, double dt) {
     else if (ctx->cfg.physics & PST_PHYS_DEM) PST_TRY(pst_dem_integrate(ctx, dt));
     ctx->nbrs_valid = false;
     ctx->eos_valid = false;
+    ctx->state_epoch++;
     return PST_OK;
 }
 

@@ -372,6 +372,8 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
             }
     }
     ctx->n = (uint64_t)(n_stay + aL + aR);
+    ctx->state_epoch++;
+    if (aL + aR > 0) ctx->uni_dirty = true;   // arrivals carry their own m and h
     *arrivals = aL + aR;
     return PST_OK;
 }
@@ -469,7 +471,7 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
             ctx->n_ghost_l = left >= 0 ? W : 0;
             ctx->n_ghost_r = right >= 0 ? W : 0;
             ctx->ghost_exact = false;
-            ctx->eos_valid = false;
+            ctx->eos_valid = false; ctx->state_epoch++;
             return PST_OK;
         }
         if (c->msg_bytes < msg) {
@@ -500,7 +502,7 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
         ctx->n_ghost_l = left >= 0 ? W : 0;
         ctx->n_ghost_r = right >= 0 ? W : 0;
         ctx->ghost_exact = false;
-        ctx->eos_valid = false;
+        ctx->eos_valid = false; ctx->state_epoch++;
         return PST_OK;
     }
     // 1. where do my edge layers start and end?  (4 table entries -> host)
@@ -559,6 +561,6 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
     ctx->n_ghost_l = nL;
     ctx->n_ghost_r = nR;
     ctx->ghost_exact = true;
-    ctx->eos_valid = false;
+    ctx->eos_valid = false; ctx->state_epoch++;
     return PST_OK;
 }

@@ -470,6 +470,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     ctx->ordered = true;
     ctx->nbrs_valid = true;
     ctx->eos_valid = false;
+    ctx->state_epoch++;
     return PST_OK;
 }
 

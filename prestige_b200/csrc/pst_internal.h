@@ -84,8 +84,16 @@ struct pst_ctx {
     bool ordered = false;            // device order != id order (a sort has happened)
     bool nbrs_valid = false;
     bool eos_valid = false;
-    bool m_uniform = false;          // every uploaded particle mass is the same value (pair kernels then skip the m[j] gather)
-    double m_value = 0.0;
+    // packed neighbour-state records of the tiled pair kernel (wcsph.cu: rec_*): valid while rec_epoch == state_epoch;
+    // everything that changes particle state (uploads, re-sorts, halo, stages, wall pressure ...) bumps state_epoch
+    void* rec = nullptr;
+    uint64_t state_epoch = 1, rec_epoch = 0;
+    // every owned particle has the same mass / smoothing length (decided on the device, pst_uniform_refresh): the tiled
+    // pair kernels then take them as constants instead of gathering m[j] and carrying the h-derived terms in registers
+    bool m_uniform = false, h_uniform = false;
+    double m_value = 0.0, h_value = 0.0;
+    bool uni_dirty = true;           // m or h may have changed since the last check (upload, pst_array pointer, new particle set)
+    unsigned long long *d_uni = nullptr, *h_uni = nullptr;   // min / max bit patterns of m and h (device, pinned mirror)
     bool hist_lag = false;           // contact-history rows still sit at their PRE-sort index (vals_out maps new -> old)
     uint64_t launches = 0;
     cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)
@@ -160,6 +168,7 @@ pst_status pst_reorder_download(pst_ctx* ctx, PstArray* a, int row, size_t n); /
 pst_status pst_iota_ids(pst_ctx* ctx);
 pst_status pst_eq1_apply(pst_ctx* ctx);                                   // eq1.cu
 pst_status pst_wcsph_eos(pst_ctx* ctx);                                   // wcsph.cu
+pst_status pst_uniform_refresh(pst_ctx* ctx);                             // wcsph.cu: are m and h uniform? (device-side reduction, once per change)
 pst_status pst_wcsph_wall_pressure(pst_ctx* ctx);                         // dummy-particle pressure extrapolation (after the EOS)
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum);
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);

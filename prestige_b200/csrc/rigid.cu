@@ -212,6 +212,7 @@ pst_status launch_scatter(pst_ctx* ctx) {
                pst_ptr<R>(ctx, "u"), pst_ptr<R>(ctx, "v"), pst_ptr<R>(ctx, "w"), pst_ptr<R>(ctx, "wx"), pst_ptr<R>(ctx, "wy"),
                pst_ptr<R>(ctx, "wz"), ctx->d_bodies);
     ctx->nbrs_valid = false;
+    ctx->state_epoch++;
     return PST_OK;
 }
 
@@ -347,7 +348,7 @@ pst_status pst_bodies_setup(pst_ctx* ctx) {
     PST_TRY(ctx->f64 ? launch_setup<double>(ctx) : launch_setup<float>(ctx));
     PST_TRY(ctx->f64 ? launch_scatter<double>(ctx) : launch_scatter<float>(ctx));
     ctx->bodies_ready = true;
-    ctx->eos_valid = false;
+    ctx->eos_valid = false; ctx->state_epoch++;
     return PST_OK;
 }
 
@@ -361,7 +362,7 @@ pst_status pst_bodies_restore(pst_ctx* ctx) {
     ctx->bodies_ready = false;
     PST_TRY(build_member_lists(ctx, false));
     ctx->bodies_ready = true;
-    ctx->eos_valid = false;
+    ctx->eos_valid = false; ctx->state_epoch++;
     return PST_OK;
 }
 

@@ -15,6 +15,8 @@
 //                       into a private list, (b) evaluates the expensive pair body only for the hits -- the exact,
 //                       FMA-free cutoff test decides there -- with all lanes busy.  Linear keys only.
 // Also here: the EOS, the dummy-particle wall pressure (k_wall_pressure) and the semi-implicit Euler stages.
+#include <cstring>
+
 #include "pst_internal.h"
 #include "wcsph_core.h"   // WcsphConst, IState, Acc, load_i, pair_body, wall_accumulate / wall_finish (shared with the host test harness)
 
@@ -22,6 +24,23 @@ namespace {
 
 constexpr int kThreads = 128;
 inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// Are the masses / smoothing lengths of the owned particles all equal?  min and max of the BIT PATTERNS (any total order
+// does: all equal <=> min == max), one atomic pair per block.
+template <class R>
+__global__ void __launch_bounds__(256) k_uniform_check(int n, const R* __restrict__ m, const R* __restrict__ h, unsigned long long* __restrict__ out) {
+    unsigned long long lo_m = ~0ull, hi_m = 0, lo_h = ~0ull, hi_h = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const unsigned long long km = (unsigned long long)__double_as_longlong((double)m[s]);
+        const unsigned long long kh = h ? (unsigned long long)__double_as_longlong((double)h[s]) : 0ull;
+        lo_m = min(lo_m, km); hi_m = max(hi_m, km); lo_h = min(lo_h, kh); hi_h = max(hi_h, kh);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        lo_m = min(lo_m, __shfl_xor_sync(0xffffffffu, lo_m, d)); hi_m = max(hi_m, __shfl_xor_sync(0xffffffffu, hi_m, d));
+        lo_h = min(lo_h, __shfl_xor_sync(0xffffffffu, lo_h, d)); hi_h = max(hi_h, __shfl_xor_sync(0xffffffffu, hi_h, d));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out, lo_m); atomicMax(out + 1, hi_m); atomicMin(out + 2, lo_h); atomicMax(out + 3, hi_h); }
+}
 
 template <class R>
 WcsphConst<R> make_const(pst_ctx* ctx) {
@@ -34,7 +53,16 @@ WcsphConst<R> make_const(pst_ctx* ctx) {
     C.beta = (R)pst_param(ctx, "beta");
     C.g[0] = (R)pst_param(ctx, "gx"); C.g[1] = (R)pst_param(ctx, "gy"); C.g[2] = (R)pst_param(ctx, "gz");
     C.gamma_is_7 = gamma == 7.0;
+    C.u_h = C.u_half_inv_h = C.u_gfc = C.u_eta2 = C.u_rc2 = (R)0;
     return C;
+}
+
+// the h-derived constants of a context whose particles all share one smoothing length: the same load_i the kernels run
+template <class R, int DIM>
+void fill_uniform(pst_ctx* ctx, WcsphConst<R>& C) {
+    IState<R, DIM> I;
+    load_i<R, DIM>(I, C, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)ctx->h_value);
+    C.u_h = I.h; C.u_half_inv_h = I.half_inv_h; C.u_gfc = I.gfc; C.u_eta2 = I.eta2; C.u_rc2 = I.rc2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -44,10 +72,36 @@ WcsphConst<R> make_const(pst_ctx* ctx) {
 // Coupled SPH-DEM contexts (DESIGN.md "Coupled formulation") also get `msph`, the SPH mass the pair kernels read in
 // place of m: +m for fluid, -m for boundaries, -m rho0/rho_solid (the displaced fluid mass) for solids.  The sign
 // carries "is fluid" into the pair loop without another gather: a pair is active iff one of its two particles is fluid.
+// Packed neighbour-state records for the tiled pair kernel (variant 3, option rec_impl = 1): blocks of 8 particles x 5
+// rows of 8 pairs -- (x,y) (z,u) (v,w) (rho, p/rho^2) (m or signed SPH mass, h) -- so one pair of the loop costs 4 (5) 16-byte
+// loads off ONE address instead of 8 (9) 8-byte loads off 8 (9) array bases; lanes of a warp that gather different j hit
+// bank group j mod 8 of the L1 data array, whatever the row.  Element (pair) index of particle j, row r: j + (j & ~7) * 4 + 8 r
+// (valid for the negative ghost indices too).
+template <class R> struct RecPair;
+template <> struct RecPair<double> { using type = double2; };
+template <> struct RecPair<float> { using type = float2; };
+constexpr int kRecRows = 5;
+// 32-bit arithmetic: the context refuses records beyond 2^31 / 5 particles (rec_alloc)
+__host__ __device__ inline int rec_index(int j) { return j + (j & ~7) * (kRecRows - 1); }
+
+template <class R>
+struct RecSrc { const R *x, *y, *z, *u, *v, *w, *rho, *por2, *m, *h; };
+
+template <class R>
+__device__ __forceinline__ void rec_store(R* __restrict__ rec, const RecSrc<R>& S, int s, R rho_s, R por2_s) {
+    using P = typename RecPair<R>::type;
+    P* q = reinterpret_cast<P*>(rec) + rec_index(s);
+    P a; a.x = S.x[s]; a.y = S.y[s]; q[0] = a;
+    a.x = S.z ? S.z[s] : (R)0; a.y = S.u[s]; q[8] = a;
+    a.x = S.v[s]; a.y = S.w ? S.w[s] : (R)0; q[16] = a;
+    a.x = rho_s; a.y = por2_s; q[24] = a;
+    a.x = S.m[s]; a.y = S.h[s]; q[32] = a;
+}
+
 template <class R>
 __global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, const R* __restrict__ rho, R* __restrict__ p,
                                              R* __restrict__ por2, const int32_t* __restrict__ tag, const R* __restrict__ m,
-                                             R* __restrict__ msph, R solid_ratio) {
+                                             R* __restrict__ msph, R solid_ratio, R* __restrict__ rec, RecSrc<R> S) {
     const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= hi) return;
     if (msph) {
@@ -58,12 +112,22 @@ __global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, co
     // (rho/rho0)^gamma - 1 without cancellation near rho0 (same form as the oracle)
     const R e = (r - C.rho0) / C.rho0;
     const R pr = C.B * expm1(C.gamma * log1p(e));
+    const R q = pr / (r * r);
     p[s] = pr;
-    por2[s] = pr / (r * r);
+    por2[s] = q;
+    if (rec) rec_store<R>(rec, S, s, r, q);      // S.m is msph in coupled contexts: written above by this same thread
+}
+
+// records alone (state changed after the EOS pass, e.g. by the wall-pressure equation, or continuity without the EOS)
+template <class R>
+__global__ void __launch_bounds__(256) k_rec_pack(int lo, int hi, R* __restrict__ rec, RecSrc<R> S) {
+    const int s = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < hi) rec_store<R>(rec, S, s, S.rho[s], S.por2[s]);
 }
 
 template <class R>
 struct ForceArgs {
+    const R* rec;   // packed records (variant 3 with rec_impl = 1), element 0 = particle 0
     R m_uni;   // UMASS kernels: the mass every particle has
     const R *x, *y, *z, *u, *v, *w, *rho, *m, *h, *por2;
     R *au, *av, *aw, *arho;
@@ -672,6 +736,33 @@ __global__ void __launch_bounds__(NT, 384 / NT) k_wcsph_cellwarp(GridDev<R> g, W
     }
 }
 
+// element 0 of the record buffer (the allocation starts ghost_cap rounded up to a block of 8 earlier)
+template <class R>
+R* rec_ptr(pst_ctx* ctx) {
+    if (!ctx->rec) return nullptr;
+    const size_t g8 = (ctx->ghost_cap + 7) & ~(size_t)7;
+    return reinterpret_cast<R*>(ctx->rec) + g8 * kRecRows * 2;
+}
+inline bool rec_wanted(pst_ctx* ctx) {
+    return !ctx->grid.morton && pst_option(ctx, "force_kernel", 2) == 3 && pst_option(ctx, "rec_impl", 1) == 1;
+}
+pst_status rec_alloc(pst_ctx* ctx) {
+    if (ctx->rec) return PST_OK;
+    if ((ctx->capacity + 2 * ctx->ghost_cap + 16) * kRecRows >= (1ull << 31)) return pst_fail(ctx, PST_EINVAL, "rec_impl = 1 supports up to 2^31 / 5 particles per context: set option rec_impl = 0");
+    const size_t g8 = (ctx->ghost_cap + 7) & ~(size_t)7;
+    const size_t elems = (g8 + ((ctx->capacity + ctx->ghost_cap + 7) & ~(size_t)7) + 8) * kRecRows * 2;
+    if (cudaMalloc(&ctx->rec, elems * (ctx->f64 ? 8 : 4)) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "neighbour-state records (%zu bytes)", elems * (ctx->f64 ? 8 : 4));
+    return PST_OK;
+}
+template <class R>
+RecSrc<R> rec_src(pst_ctx* ctx) {
+    RecSrc<R> S;
+    S.x = pst_ptr<R>(ctx, "x"); S.y = pst_ptr<R>(ctx, "y"); S.z = pst_ptr<R>(ctx, "z");
+    S.u = pst_ptr<R>(ctx, "u"); S.v = pst_ptr<R>(ctx, "v"); S.w = pst_ptr<R>(ctx, "w");
+    S.rho = pst_ptr<R>(ctx, "rho"); S.por2 = pst_ptr<R>(ctx, "por2"); S.m = pst_ptr<R>(ctx, ctx->coupled ? "msph" : "m"); S.h = pst_ptr<R>(ctx, "h");
+    return S;
+}
+
 template <class R>
 ForceArgs<R> make_args(pst_ctx* ctx) {
     ForceArgs<R> A;
@@ -682,6 +773,7 @@ ForceArgs<R> make_args(pst_ctx* ctx) {
     A.cell_start = ctx->cell_start;
     A.n = (int)ctx->n;
     A.m_uni = (R)ctx->m_value;
+    A.rec = rec_ptr<R>(ctx);
     return A;
 }
 
@@ -754,6 +846,7 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
     // all masses equal (seen at upload): the fused kernel without the m[j] gather.  With a communicator the ghosts and the
     // migrants come from other ranks, whose uploads this rank has not seen: the caller vouches for them with the option
     // "uniform_mass_global" = 1 (every rank uploaded the same single mass value; bench.py checks it with an all-reduce).
+    PST_TRY(pst_uniform_refresh(ctx));
     const bool umass = VARIANT == 2 && ctx->m_uniform && (!ctx->comm || pst_option(ctx, "uniform_mass_global", 0) != 0) &&
                        pst_option(ctx, "uniform_mass", 1) != 0;
     if constexpr (VARIANT == 2) {
@@ -762,6 +855,17 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
     if (cont && mom) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, true>(ctx, T, smem);
     if (cont) return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, true, false>(ctx, T, smem);
     return launch_tiled_k<R, DIM, TA, TB, NT, VARIANT, false, true>(ctx, T, smem);
+}
+
+// bring the packed records up to date (no-op when the EOS pass has just written them)
+template <class R>
+pst_status rec_refresh(pst_ctx* ctx) {
+    if (ctx->rec && ctx->rec_epoch == ctx->state_epoch) return PST_OK;
+    PST_TRY(rec_alloc(ctx));
+    const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r;
+    if (hi > lo) PST_LAUNCH(ctx, k_rec_pack<R>, blocks_for(hi - lo, 256), 256, 0, lo, hi, rec_ptr<R>(ctx), rec_src<R>(ctx));
+    ctx->rec_epoch = ctx->state_epoch;
+    return PST_OK;
 }
 
 #include "wcsph_zrun.cuh"   // variant 3: tiles + fine z-runs + bit masks
@@ -870,9 +974,13 @@ pst_status launch_eos(pst_ctx* ctx) {
     if (hi <= lo) return PST_OK;
     const double rs = pst_param(ctx, "rho_solid", 0.0);
     if (ctx->coupled && !(rs > 0)) return pst_fail(ctx, PST_EINVAL, "coupled context: parameter rho_solid must be > 0");
+    const bool pack = rec_wanted(ctx);
+    if (pack) PST_TRY(rec_alloc(ctx));
     PST_LAUNCH(ctx, k_eos<R>, blocks_for(hi - lo, 256), 256, 0, make_const<R>(ctx), lo, hi, pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "p"),
                pst_ptr<R>(ctx, "por2"), ctx->coupled ? pst_ptr<int32_t>(ctx, "tag") : nullptr, pst_ptr<R>(ctx, "m"),
-               ctx->coupled ? pst_ptr<R>(ctx, "msph") : nullptr, ctx->coupled ? (R)pst_param(ctx, "rho0") / (R)rs : (R)0);
+               ctx->coupled ? pst_ptr<R>(ctx, "msph") : nullptr, ctx->coupled ? (R)pst_param(ctx, "rho0") / (R)rs : (R)0,
+               pack ? rec_ptr<R>(ctx) : nullptr, rec_src<R>(ctx));
+    if (pack) ctx->rec_epoch = ctx->state_epoch;
     return PST_OK;
 }
 
@@ -956,7 +1064,34 @@ pst_status launch_wall_pressure(pst_ctx* ctx) {
 pst_status pst_wcsph_wall_pressure(pst_ctx* ctx) {
     if (ctx->n == 0) return PST_OK;
     if (ctx->comm) return pst_fail(ctx, PST_EINVAL, "wall_pressure is single-GPU for now: ghost dummy particles would need a second density exchange");
+    ctx->state_epoch++;     // rho, p, p/rho^2 of the non-fluid rows change: packed records are stale
     return PST_DISPATCH(ctx, launch_wall_pressure, ctx);
+}
+
+pst_status pst_uniform_refresh(pst_ctx* ctx) {
+    if (!ctx->uni_dirty) return PST_OK;
+    ctx->m_uniform = ctx->h_uniform = false;
+    const int n = (int)ctx->n;
+    PstArray* m = pst_find(ctx, "m");
+    if (n == 0 || !m) { ctx->uni_dirty = false; return PST_OK; }
+    if (!ctx->d_uni) {
+        PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_uni, 4 * sizeof(unsigned long long)));
+        PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_uni, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    ctx->h_uni[0] = ctx->h_uni[2] = ~0ull; ctx->h_uni[1] = ctx->h_uni[3] = 0ull;
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->d_uni, ctx->h_uni, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = std::min(blocks_for(n, 256), 1184u);
+    if (ctx->f64) PST_LAUNCH(ctx, k_uniform_check<double>, grid, 256, 0, n, pst_ptr<double>(ctx, "m"), pst_ptr<double>(ctx, "h"), ctx->d_uni);
+    else PST_LAUNCH(ctx, k_uniform_check<float>, grid, 256, 0, n, pst_ptr<float>(ctx, "m"), pst_ptr<float>(ctx, "h"), ctx->d_uni);
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_uni, ctx->d_uni, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // once per change of m / h, not per step
+    auto as_double = [](unsigned long long k) { double d; std::memcpy(&d, &k, sizeof d); return d; };
+    ctx->m_uniform = ctx->h_uni[0] == ctx->h_uni[1];
+    ctx->m_value = as_double(ctx->h_uni[0]);
+    ctx->h_uniform = pst_find(ctx, "h") && ctx->h_uni[2] == ctx->h_uni[3];
+    ctx->h_value = as_double(ctx->h_uni[2]);
+    ctx->uni_dirty = false;
+    return PST_OK;
 }
 
 pst_status pst_wcsph_eos(pst_ctx* ctx) {

@@ -40,6 +40,9 @@ template <class R>
 struct WcsphConst {
     R kfac, rho0, c0, gamma, B, alpha_c0, beta, g[3];
     int gamma_is_7;
+    // UNI kernels (every particle has the same smoothing length and mass): the h-derived constants of IState, computed
+    // once on the host by the same load_i, so they cost constant-bank operands instead of ten registers per thread
+    R u_h, u_half_inv_h, u_gfc, u_eta2, u_rc2;
 };
 
 template <class R, int DIM>
@@ -106,12 +109,13 @@ PST_HD float fast_rcp(float x) {
 
 // the pair body (continuity then momentum, the order fuse() keeps: fuse.rs:18,30).
 // caller has already established 0 < r2 < rc2 with the exact test.  Branch-free: one rsqrt, one rcp.
-template <class R, int DIM, bool CONT, bool MOM>
+template <class R, int DIM, bool CONT, bool MOM, bool UNI = false>
 PST_HD void pair_body(const WcsphConst<R>& C, const IState<R, DIM>& I, R dx, R dy, R dz, R r2, R uj, R vj, R wj,
                       R rhoj, R mj, R por2j, Acc<R>& a) {
+    const R half_inv_h = UNI ? C.u_half_inv_h : I.half_inv_h, gfc = UNI ? C.u_gfc : I.gfc, eta2 = UNI ? C.u_eta2 : I.eta2, h = UNI ? C.u_h : I.h;
     const R r = r2 * fast_rsqrt(r2);
-    const R t = (R)1 - r * I.half_inv_h;
-    const R gf = I.gfc * (t * t * t);
+    const R t = (R)1 - r * half_inv_h;
+    const R gf = gfc * (t * t * t);
     const R du = I.u - uj, dv = I.v - vj, dw = DIM == 3 ? I.w - wj : (R)0;
     R vx = du * dx + dv * dy;
     if (DIM == 3) vx += dw * dz;
@@ -120,8 +124,8 @@ PST_HD void pair_body(const WcsphConst<R>& C, const IState<R, DIM>& I, R dx, R d
     if (MOM) {
         // Pi = (beta mu - alpha c0) mu / rho_bar,  mu = h vx / (r2 + eta2),  rho_bar = (rho_i + rho_j)/2
         const R rhos = I.rho + rhoj;
-        const R inv = fast_rcp((r2 + I.eta2) * rhos);
-        const R wv = I.h * vx * inv;                        // mu / (2 rho_bar)
+        const R inv = fast_rcp((r2 + eta2) * rhos);
+        const R wv = h * vx * inv;                          // mu / (2 rho_bar)
         const R mu = wv * rhos;
         const R Pi = vx < (R)0 ? (C.beta * mu - C.alpha_c0) * (wv + wv) : (R)0;
         const R c = -mgf * (I.por2 + por2j + Pi);

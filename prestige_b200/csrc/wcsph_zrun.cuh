@@ -26,12 +26,11 @@ struct ZTile {
     int maxw;        // mask words per thread
 };
 
-constexpr int kZJcap = 2304;   // staged candidates per tile (12 B each = 27 KB)
 constexpr int kZPad = 64;      // readable slack behind the staged rows: lanes with a short range over-scan with the warp
-constexpr int kZRow = kZJcap + kZPad;
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UMASS = false>
-__global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, ZTile T) {
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false, bool REC = false, int MINB = 2, int JC = 2304, int DBG = 0>
+__global__ void __launch_bounds__(NT, MINB) k_wcsph_zrun(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, ZTile T) {
+    constexpr int kZJcap = JC, kZRow = JC + kZPad;   // staged candidates per tile (12 B each)
     using D = TileDims<DIM, TA, TB>;
     constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
     constexpr int NW = NT / 32;
@@ -53,6 +52,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_z + (DIM == 3 ? kZRow : 0));   // maxw * NT
     int* s_base = reinterpret_cast<int*>(s_mask + T.maxw * NT);                      // maxw * NT: global index of a word's first candidate
 
+    using P2 = typename RecPair<R>::type;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- which tile
     int b = blockIdx.x;
@@ -170,14 +170,21 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R
         if (active) {
             while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
             gi = s_ibeg[c] + (ii - s_ipre[c]);
-            if (COUPLED) fluid_i = A.m[gi] > (R)0;
             lx = c / BB; ly = c - lx * BB;
-            load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
-                           A.por2[gi], A.h[gi]);
+            if (REC) {
+                const P2* q = reinterpret_cast<const P2*>(A.rec) + rec_index(gi);
+                const P2 r0 = q[0], r1 = q[8], r2 = q[16], r3 = q[24], r4 = q[32];
+                if (COUPLED) fluid_i = r4.x > (R)0;
+                load_i<R, DIM>(I, C, r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, r4.y);
+            } else {
+                if (COUPLED) fluid_i = A.m[gi] > (R)0;
+                load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
+                               A.por2[gi], A.h[gi]);
+            }
             xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
             // conservative f32 pre-filter: relative margin 2^-15 on rc^2 (>> the f32 error of tile-local coordinates, see
             // launch_zrun); the range cull below uses twice that
-            rc2f = __double2float_ru((double)I.rc2 * (1.0 + 1.0 / 32768.0));
+            rc2f = __double2float_ru((double)(UNI ? C.u_rc2 : I.rc2) * (1.0 + 1.0 / 32768.0));
             rc2m = rc2f * (1.0f + 1.0f / 16384.0f);
         }
         const float fz = DIM == 3 ? zf : yf;            // coordinate along the fast axis, relative to fine cell f0
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R
             int nw = 0, nch = 0;
             while (k < NRUN) {
                 open_run(k);
-                const int a4 = vs & ~3;
+                int a4 = vs & ~3;
                 const int ng = (ve - a4 + 3) >> 2;
                 const int Tg = __reduce_max_sync(0xffffffffu, ve > vs ? ng : 0);   // the warp scans its longest range
                 bool full = false;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R
                     const int j0 = a4 + wc * 32;
                     const float* px = s_x + min(j0, kZRow - 32);           // (only a lane past its own range is ever clamped)
                     unsigned m = 0;
-#pragma unroll 2
+#pragma unroll 4
                     for (int it = 0; it < iters; ++it, px += 4) {
                         const float4 X = *reinterpret_cast<const float4*>(px), Y = *reinterpret_cast<const float4*>(px + kZRow);
                         const float4 Z = DIM == 3 ? *reinterpret_cast<const float4*>(px + 2 * kZRow) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -263,36 +270,63 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R
             }
             // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
             {
-                int w = 0, base = 0;
+                // hit iterator over the mask words (none of them empty): m = bits left in the current word, base31 = global index
+                // of its first candidate + 31, w = next word
+                int w = 0, base31 = 0;
                 unsigned m = 0;
-                auto next = [&](int& j) -> bool {
-                    while (m == 0) {
-                        if (w >= nw) return false;
-                        m = my_mask[w * NT]; base = my_base[w * NT]; ++w;
-                    }
-                    const int cz = __clz(m);
-                    m &= ~(0x80000000u >> cz);
-                    j = base + cz;
-                    return true;
+                if (nw > 0 && DBG != 3) { m = my_mask[0]; base31 = my_base[0] + 31; w = 1; }
+                if (DBG == 3) a.au += (R)nw;      // timing ablation: phase 1 only
+                auto pop = [&]() -> int {      // requires m != 0
+                    const int msb = 31 - __clz(m);
+                    int j = base31 - msb;
+                    asm("" : "+r"(j));        // keep j a plain 32-bit value: the record index below is 32-bit arithmetic + one IMAD.WIDE
+                    m ^= 1u << msb;
+                    if (m == 0 && w < nw) { m = my_mask[w * NT]; base31 = my_base[w * NT] + 31; ++w; }
+                    return j;
                 };
-                while (true) {
-                    int j0, j1;
-                    if (!next(j0)) break;
-                    const bool v1 = next(j1);
-                    if (!v1) j1 = j0;
-                    const R dx0 = I.x - A.x[j0], dy0 = I.y - A.y[j0], dz0 = DIM == 3 ? I.z - A.z[j0] : (R)0;
-                    const R dx1 = I.x - A.x[j1], dy1 = I.y - A.y[j1], dz1 = DIM == 3 ? I.z - A.z[j1] : (R)0;
+                while (m != 0) {
+                    const int j0 = pop();
+                    const bool v1 = m != 0;
+                    const int j1 = v1 ? pop() : j0;
+                    R xj0, yj0, zj0, uj0, vj0, wj0, rj0, pj0, xj1, yj1, zj1, uj1, vj1, wj1, rj1, pj1, mj0 = A.m_uni, mj1 = A.m_uni;
+                    const R rc2 = UNI ? C.u_rc2 : I.rc2;
+                    if (DBG == 1) {     // timing ablation (wrong results): no gathers, the j state is made up from the index
+                        xj0 = I.x + (R)(j0 & 15) * (R)1e-3; yj0 = I.y + (R)(j0 & 7) * (R)1e-3; zj0 = I.z; uj0 = I.u; vj0 = I.v; wj0 = (R)j0; rj0 = I.rho; pj0 = I.por2;
+                        xj1 = I.x + (R)(j1 & 15) * (R)1e-3; yj1 = I.y + (R)(j1 & 7) * (R)1e-3; zj1 = I.z; uj1 = I.u; vj1 = I.v; wj1 = (R)j1; rj1 = I.rho; pj1 = I.por2;
+                    } else if (REC) {
+                        const P2* q0 = reinterpret_cast<const P2*>(A.rec) + rec_index(j0);
+                        const P2* q1 = reinterpret_cast<const P2*>(A.rec) + rec_index(j1);
+                        const P2 a0 = q0[0], b0 = q0[8], a1 = q1[0], b1 = q1[8];
+                        P2 c0, d0, c1, d1;
+                        if (DBG == 4) { c0.x = I.v; c0.y = I.w; d0.x = I.rho; d0.y = I.por2; c1 = c0; d1 = d0; }   // timing ablation: half the gather
+                        else { c0 = q0[16]; d0 = q0[24]; c1 = q1[16]; d1 = q1[24]; }
+                        xj0 = a0.x; yj0 = a0.y; zj0 = b0.x; uj0 = b0.y; vj0 = c0.x; wj0 = c0.y; rj0 = d0.x; pj0 = d0.y;
+                        xj1 = a1.x; yj1 = a1.y; zj1 = b1.x; uj1 = b1.y; vj1 = c1.x; wj1 = c1.y; rj1 = d1.x; pj1 = d1.y;
+                        if (!UNI) { mj0 = q0[32].x; mj1 = q1[32].x; }
+                    } else {
+                        xj0 = A.x[j0]; yj0 = A.y[j0]; zj0 = DIM == 3 ? A.z[j0] : (R)0; uj0 = A.u[j0]; vj0 = A.v[j0]; wj0 = DIM == 3 ? A.w[j0] : (R)0;
+                        rj0 = A.rho[j0]; pj0 = A.por2[j0];
+                        xj1 = A.x[j1]; yj1 = A.y[j1]; zj1 = DIM == 3 ? A.z[j1] : (R)0; uj1 = A.u[j1]; vj1 = A.v[j1]; wj1 = DIM == 3 ? A.w[j1] : (R)0;
+                        rj1 = A.rho[j1]; pj1 = A.por2[j1];
+                        if (!UNI) { mj0 = A.m[j0]; mj1 = A.m[j1]; }
+                    }
+                    if (DBG == 2) {     // timing ablation (wrong results): gathers only, no pair body
+                        a.au += xj0 + yj0 + zj0 + uj0; a.av += vj0 + wj0 + rj0 + pj0; a2.au += xj1 + yj1 + zj1 + uj1; a2.av += vj1 + wj1 + rj1 + pj1;
+                        continue;
+                    }
+                    const R dx0 = I.x - xj0, dy0 = I.y - yj0, dz0 = DIM == 3 ? I.z - zj0 : (R)0;
+                    const R dx1 = I.x - xj1, dy1 = I.y - yj1, dz1 = DIM == 3 ? I.z - zj1 : (R)0;
                     R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
-                    const bool in0 = r20 < I.rc2 && r20 > (R)0;            // the exact test (the set is defined here)
-                    const bool in1 = v1 && r21 < I.rc2 && r21 > (R)0;
+                    const bool in0 = r20 < rc2 && r20 > (R)0;              // the exact test (the set is defined here)
+                    const bool in1 = v1 && r21 < rc2 && r21 > (R)0;
                     r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
-                    R m0 = in0 ? (UMASS ? A.m_uni : A.m[j0]) : (R)0, m1 = in1 ? (UMASS ? A.m_uni : A.m[j1]) : (R)0;
+                    R m0 = in0 ? mj0 : (R)0, m1 = in1 ? mj1 : (R)0;
                     if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
                         m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
                         m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
                     }
-                    pair_body<R, DIM, CONT, MOM>(C, I, dx0, dy0, dz0, r20, A.u[j0], A.v[j0], DIM == 3 ? A.w[j0] : (R)0, A.rho[j0], m0, A.por2[j0], a);
-                    pair_body<R, DIM, CONT, MOM>(C, I, dx1, dy1, dz1, r21, A.u[j1], A.v[j1], DIM == 3 ? A.w[j1] : (R)0, A.rho[j1], m1, A.por2[j1], a2);
+                    pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx0, dy0, dz0, r20, uj0, vj0, wj0, rj0, m0, pj0, a);
+                    pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx1, dy1, dz1, r21, uj1, vj1, wj1, rj1, m1, pj1, a2);
                 }
             }
             if (k == NRUN) break;      // warp-uniform
@@ -304,18 +338,29 @@ __global__ void __launch_bounds__(NT, 2) k_wcsph_zrun(GridDev<R> g, WcsphConst<R
     }
 }
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UMASS = false>
+template <class R, int DIM, int TA, int TB, int NT, int MINB, int JC, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false>
 pst_status launch_zrun_k(pst_ctx* ctx, const ZTile& T, size_t smem) {
-    auto kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UMASS>;
+    const bool rec = rec_wanted(ctx);
+    if (rec) PST_TRY(rec_refresh<R>(ctx));
+    auto kern = rec ? k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC> : k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, false, MINB, JC>;
+    if (UNI && rec && CONT && MOM && !COUPLED && DIM == 3 && MINB == 2) {     // timing ablations of the headline kernel (wrong results)
+        const int dbg = pst_option(ctx, "tile_dbg", 0);
+        if (dbg == 1) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 1>;
+        if (dbg == 2) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 2>;
+        if (dbg == 3) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 3>;
+        if (dbg == 4) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 4>;
+    }
     PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const unsigned grid = (unsigned)T.tiles[0] * T.tiles[1] * T.tiles[2];
-    PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), make_args<R>(ctx), T);
+    WcsphConst<R> C = make_const<R>(ctx);
+    if (UNI) fill_uniform<R, DIM>(ctx, C);
+    PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), C, make_args<R>(ctx), T);
     return PST_OK;
 }
 
-template <class R, int DIM>
-pst_status launch_zrun(pst_ctx* ctx, bool cont, bool mom) {
-    constexpr int TA = 2, TB = 2, NT = 256;
+template <class R, int DIM, int TA, int TB, int NT, int MINB, int JC>
+pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
+    constexpr int kZJcap = JC, kZRow = JC + kZPad;
     using D = TileDims<DIM, TA, TB>;
     const PstGrid& g = ctx->grid;
     const int S = g.sub;
@@ -324,9 +369,9 @@ pst_status launch_zrun(pst_ctx* ctx, bool cont, bool mom) {
     if (!(ppc > 0)) ppc = DIM == 3 ? 14.0 : 6.0;
     ZTile T;
     T.maxw = pst_option(ctx, "tile_words", 16);
-    const int user_G = pst_option(ctx, "tile_g", 0);   // in COARSE cells
+    const int user_G = pst_option(ctx, "tile_g", 0) * S + pst_option(ctx, "tile_gf", 0);   // tile_g in COARSE cells, tile_gf in fine cells
     // tile depth in fine cells: about one thread per particle
-    int GF = user_G > 0 ? user_G * S : (int)std::floor(0.95 * NT * S / (D::NI * ppc));
+    int GF = user_G > 0 ? user_G : (int)std::floor(0.95 * NT * S / (D::NI * ppc));
     GF = std::min(std::max(GF, 1), std::max(1, nf));
     // f32 pre-filter: tile-local coordinates reach (GF / S + 2 + TA) cells (see test_prefilter_margin.py: <= 32 cells keeps the
     // f32 error of r^2 below half of the 2^-15 margin)
@@ -342,12 +387,24 @@ pst_status launch_zrun(pst_ctx* ctx, bool cont, bool mom) {
     const size_t smem = ints + (size_t)(DIM == 3 ? 3 : 2) * kZRow * sizeof(float) + (size_t)T.maxw * NT * 8;
     if (smem > 227 * 1024) return pst_fail(ctx, PST_EINVAL, "tile_words too large");
     if (ctx->coupled) {
-        if (DIM == 3) return launch_zrun_k<R, 3, TA, TB, NT, true, true, true>(ctx, T, smem);
+        if (DIM == 3) return launch_zrun_k<R, 3, TA, TB, NT, MINB, JC, true, true, true>(ctx, T, smem);
         return pst_fail(ctx, PST_EINVAL, "coupled contexts need dim = 3");
     }
-    const bool umass = ctx->m_uniform && (!ctx->comm || pst_option(ctx, "uniform_mass_global", 0) != 0) && pst_option(ctx, "uniform_mass", 1) != 0;
-    if (cont && mom && umass) return launch_zrun_k<R, DIM, TA, TB, NT, true, true, false, true>(ctx, T, smem);
-    if (cont && mom) return launch_zrun_k<R, DIM, TA, TB, NT, true, true>(ctx, T, smem);
-    if (cont) return launch_zrun_k<R, DIM, TA, TB, NT, true, false>(ctx, T, smem);
-    return launch_zrun_k<R, DIM, TA, TB, NT, false, true>(ctx, T, smem);
+    // every particle this rank can see has the same mass AND smoothing length (owned ones: checked on the device; ghosts and
+    // migrants of other ranks: the caller vouches for them with "uniform_mass_global"): both become kernel constants
+    PST_TRY(pst_uniform_refresh(ctx));
+    const bool uni = ctx->m_uniform && ctx->h_uniform && (!ctx->comm || pst_option(ctx, "uniform_mass_global", 0) != 0) && pst_option(ctx, "uniform_mass", 1) != 0;
+    if (cont && mom && uni) return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, true, true, false, true>(ctx, T, smem);
+    if (cont && mom) return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, true, true>(ctx, T, smem);
+    if (cont) return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, true, false>(ctx, T, smem);
+    return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, false, true>(ctx, T, smem);
+}
+
+template <class R, int DIM>
+pst_status launch_zrun(pst_ctx* ctx, bool cont, bool mom) {
+    // 2 x 2 columns, 256 threads, two CTAs per SM.  Measured and dropped (profiles/r2_exp_log.txt): 4 x 2 columns with 512 threads
+    // and one CTA per SM (+6 %), three CTAs per SM at 80 registers (+12..21 %: spills, and the third CTA's shared memory leaves too
+    // little L1 for the gathers), prefetch.global.L1 of the next trip's records (+25 %)
+    if (pst_option(ctx, "tile_jc", 0) == 1) return launch_zrun_shape<R, DIM, 2, 2, 256, 2, 1664>(ctx, cont, mom);
+    return launch_zrun_shape<R, DIM, 2, 2, 256, 2, 2304>(ctx, cont, mom);
 }

@@ -58,8 +58,9 @@ def parity():
             ref = orc.wcsph(dim, br.params, a, grid=g)
             refp, _ = orc.pairs(dim, a["x"], a["y"], a.get("z"), a["h"], grid=g)
             tol = 1e-10 if real == np.float64 else 1e-5
-            for variant, zsub, opts in [(0, 1, None), (0, 4, None), (3, 1, None), (3, 2, None), (3, 4, None), (3, 8, None),
-                                        (3, 4, {"tile_words": 4}), (3, 4, {"tile_g": 1}), (3, 4, {"tile_jcap": 100}), (3, 4, {"uniform_mass": 0})]:
+            for variant, zsub, opts in [(0, 4, None), (3, 1, None), (3, 4, None), (3, 8, {"rec_impl": 0}), (3, 4, {"rec_impl": 0}),
+                                        (3, 4, {"tile_words": 4}), (3, 4, {"tile_g": 1}), (3, 4, {"tile_jcap": 100}), (3, 4, {"uniform_mass": 0}),
+                                        (3, 2, {"uniform_mass": 0, "rec_impl": 0})]:
                 try:
                     got, pairs = run(b, real, variant, zsub, opts)
                     errs = {k: rel_err(got[k], ref[k]) for k in got}
@@ -80,7 +81,7 @@ def timing(shape=(200, 200, 250)):
     b = synth.wcsph_block_3d(*shape)
     say(f"timing block {shape}: {b.n} particles")
     base = None
-    for variant, zsub, opts in [(2, 1, {}), (3, 1, {}), (3, 2, {}), (3, 4, {}), (3, 8, {}), (3, 4, {"tile_words": 12}), (3, 4, {"tile_words": 24})]:
+    for variant, zsub, opts in [(3, 4, {}), (3, 4, {"tile_gf": 16}), (3, 4, {"tile_gf": 15}), (3, 4, {"tile_gf": 16, "tile_jc": 1}), (3, 4, {"tile_gf": 16, "tile_jc": 1, "tile_words": 12}), (3, 4, {"tile_gf": 32, "tile_jc": 0})]:
         ctx = pb.context_for_block(b)
         try:
             ctx.set_option("zsub", zsub)
@@ -98,13 +99,13 @@ def timing(shape=(200, 200, 250)):
                 return (time.perf_counter() - t0) / reps * 1e3
             ctx.build_neighbours(); ctx.apply(["tait_eos"]); ctx.apply(["continuity", "momentum"]); ctx.sync()
             t_n = stage(ctx.build_neighbours)
-            ctx.apply(["tait_eos"])
+            t_e = stage(lambda: ctx.apply(["tait_eos"]))
             t_f = stage(lambda: ctx.apply(["continuity", "momentum"]))
             au = ctx.download("au")
             if base is None:
                 base = au
             d = float(np.max(np.abs(au - base)) / np.sqrt(np.mean(base ** 2)))
-            say(f"variant {variant} zsub {zsub} {opts}: nnps {t_n:.3f} ms  pair kernel {t_f:.3f} ms  (au vs variant 2: {d:.1e})")
+            say(f"variant {variant} zsub {zsub} {opts}: nnps {t_n:.3f} ms  eos {t_e:.3f} ms  pair kernel {t_f:.3f} ms  (au vs variant 2: {d:.1e})")
         finally:
             ctx.close()
 
