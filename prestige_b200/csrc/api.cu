@@ -82,6 +82,7 @@ pst_status pst_grid_finalize(pst_ctx* ctx) {
         while ((1ull << g.key_bits) < g.ncells) ++g.key_bits;
     }
     ctx->nbrs_valid = false;
+    ctx->build_epoch++;
     ctx->params.erase("_ppc");
     return pst_nnps_alloc_table(ctx);
 }
@@ -157,6 +158,9 @@ pst_status pst_create(const pst_config* cfg, pst_ctx** out) {
                    {"gx", 0.0}, {"gy", 0.0}, {"gz", 0.0}, {"dem_model", 0.0}, {"kn", 1e5}, {"gn", 0.0}, {"kt", 2e4},
                    {"gt", 0.0}, {"mu", 0.5}, {"dt", 1e-6}, {"Estar", 1e7}, {"Gstar", 4e6}, {"erest", 0.8}, {"rho_solid", 2500.0},
                    {"boundary_model", 0.0}};   // 1: dummy-particle wall pressure in pst_step, wall density slaved
+    // fast-axis subdivision of the cell grid (option "zsub"): the tiled WCSPH pair kernel (force_kernel 3, the default) scans
+    // z-trimmed runs and wants fine cells; DEM-only contexts keep whole cells (a cell holds about one sphere)
+    ctx->grid.sub = ((cfg->physics & PST_PHYS_WCSPH) && cfg->key == PST_KEY_LINEAR) ? 4 : 1;
     pst_status s = pst_grid_finalize(ctx);   // grid + cell table
     if (s != PST_OK) return bail(s);
     auto mk = [&](const char* name, int dt, uint32_t fl, int rows = 1) { if (s == PST_OK) s = array_create(ctx, name, dt, fl, rows); };
@@ -199,7 +203,7 @@ void pst_destroy(pst_ctx* ctx) {
     pst_comm_destroy(ctx);
     for (auto& a : ctx->arrays) { cudaFree(a.buf[0]); if (a.buf[1]) cudaFree(a.buf[1]); }
     cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_in); cudaFree(ctx->vals_out);
-    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->wp_pos); cudaFree(ctx->wp_idx); cudaFree(ctx->rec); cudaFree(ctx->d_uni); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
+    cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->wp_pos); cudaFree(ctx->wp_idx); cudaFree(ctx->rec); cudaFree(ctx->ztiles); cudaFree(ctx->d_ztile_count); cudaFree(ctx->d_uni); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
     cudaFree(ctx->d_counters);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);

@@ -471,6 +471,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     ctx->nbrs_valid = true;
     ctx->eos_valid = false;
     ctx->state_epoch++;
+    ctx->build_epoch++;
     return PST_OK;
 }
 

@@ -88,6 +88,11 @@ struct pst_ctx {
     // everything that changes particle state (uploads, re-sorts, halo, stages, wall pressure ...) bumps state_epoch
     void* rec = nullptr;
     uint64_t state_epoch = 1, rec_epoch = 0;
+    // tile list of the variant-3 pair kernel (wcsph_zrun.cuh): rebuilt when the cell table changed (build_epoch)
+    void* ztiles = nullptr;
+    size_t ztiles_cap = 0, ztile_off_cap = 0;
+    int* d_ztile_count = nullptr;
+    uint64_t ztiles_key = 0, build_epoch = 1;
     // every owned particle has the same mass / smoothing length (decided on the device, pst_uniform_refresh): the tiled
     // pair kernels then take them as constants instead of gathering m[j] and carrying the h-derived terms in registers
     bool m_uniform = false, h_uniform = false;

@@ -744,7 +744,7 @@ R* rec_ptr(pst_ctx* ctx) {
     return reinterpret_cast<R*>(ctx->rec) + g8 * kRecRows * 2;
 }
 inline bool rec_wanted(pst_ctx* ctx) {
-    return !ctx->grid.morton && pst_option(ctx, "force_kernel", 2) == 3 && pst_option(ctx, "rec_impl", 1) == 1;
+    return !ctx->grid.morton && pst_option(ctx, "force_kernel", 3) == 3 && pst_option(ctx, "rec_impl", 1) == 1;
 }
 pst_status rec_alloc(pst_ctx* ctx) {
     if (ctx->rec) return PST_OK;
@@ -872,7 +872,7 @@ pst_status rec_refresh(pst_ctx* ctx) {
 
 template <class R, int DIM, bool MORTON>
 pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
-    int variant = pst_option(ctx, "force_kernel", 2);   // 3 = tiled z-runs + bit masks, 2 = thread-per-particle lists, 1 = warp-per-cell, 0 = gather
+    int variant = pst_option(ctx, "force_kernel", 3);   // 3 = tiled z-runs + bit masks (default), 2 = thread-per-particle lists, 1 = warp-per-cell, 0 = gather
     if (ctx->coupled && variant == 1) variant = 2;      // the warp-per-cell kernel has no coupled form
     if (variant == 3 && !MORTON) return launch_zrun<R, DIM>(ctx, cont, mom);
     if ((variant == 1 || variant == 2) && !MORTON && ctx->grid.sub != 1)

@@ -1,5 +1,5 @@
 // wcsph_zrun.cuh -- variant 3 of the fused continuity + momentum pair kernel (option force_kernel = 3).  Included by
-// wcsph.cu inside its anonymous namespace (it shares ForceArgs, gather_one, TileDims with the other variants).
+// wcsph.cu inside its anonymous namespace (it shares ForceArgs, gather_one, TileDims, the packed records with the rest).
 // No reference code exists for the physics; the loop shape it honours is the reference's
 // gather -- write only [i], bodies of a fused set in ONE i,j loop (prestige/src/codegen/simple_cpu.rs:7-16, fuse.rs:14-40).
 //
@@ -15,352 +15,463 @@
 //   * all lanes of a warp scan a run in lock-step (trip count = the warp's longest range, the surplus bits are cut off),
 //     every LDS.128 is 16-byte aligned by construction (runs are staged at multiples of 4, ranges start aligned down);
 //   * staging holds 12 B per candidate (f32 tile-local x, y, z; the global index follows from the word's base);
-//   * the tile preamble is parallel (warp-shuffle scans, one warp per staged run, geometric tile origin: no global load on
-//     the critical path).
-// The pair bodies (phase 2) are unchanged: the exact FMA-free test decides membership, so the neighbour set stays bit-exact.
+//   * the neighbour state of a hit comes from packed AoSoA records (wcsph.cu rec_*): 4 x LDG.128 off one address;
+//   * tiles are cut by a small kernel from the cell table so that every tile holds at most one particle per thread and
+//     nearly that many (k_ztile_list: greedy along the fast axis, empty stretches skipped);
+//   * CTAs are PERSISTENT and double-buffered: while the warps of a CTA evaluate tile n, each warp that finishes stages its
+//     share of tile n + 1 into the other buffer -- the table look-ups and the staging loads overlap the pair bodies of the
+//     other warps instead of idling the SM at the head of every CTA (one __syncthreads per tile).
+// The pair bodies (phase 2) are those of variant 2: the exact FMA-free test decides membership, so the neighbour set stays
+// bit-exact.
 
 struct ZTile {
-    int GF;          // fine cells per tile along the fast axis
-    int tiles[3];    // tile grid: [0] columns-x, [1] columns-y (1 in 2D), [2] fast axis
+    int gfcap;       // deepest tile, in fine cells
+    int wmax;        // fine-cell boundaries per staged run at that depth: gfcap + 2 sub + 1
     int jcap;        // staged-candidate capacity (<= kZJcap; tests shrink it to force the fallback)
     int maxw;        // mask words per thread
+    const int4* tiles;   // (tx, ty, f0, gf) per tile
+    const int* ntiles;   // device-side count
+    int* next;           // dynamic tile counter (starts at 2 x grid: the first two tiles of every CTA are static)
 };
 
 constexpr int kZPad = 64;      // readable slack behind the staged rows: lanes with a short range over-scan with the warp
+template <int NT> constexpr int zjcap() { return NT >= 256 ? 1536 : 1024; }   // staged candidates per buffer (12 B each)
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false, bool REC = false, int MINB = 2, int JC = 2304, int DBG = 0>
-__global__ void __launch_bounds__(NT, MINB) k_wcsph_zrun(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, ZTile T) {
-    constexpr int kZJcap = JC, kZRow = JC + kZPad;   // staged candidates per tile (12 B each)
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+// ---- tile list: one warp per tile column pair (tx, ty); greedy cut along the fast axis so that a tile holds <= target particles
+// of its own and its staged runs (own columns + one column around, `sub` fine cells above and below) hold <= jcap candidates
+template <int DIM, int TA, int TB>
+__global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, int cx_lo, int cx_hi, int tiles_x, int tiles_y, int target, int gfcap,
+                                                    int sub, int jcap, const int32_t* __restrict__ cs, int4* __restrict__ tiles, int* __restrict__ off, int write) {
+    constexpr int BB = DIM == 3 ? TB : 1;
+    constexpr int NRX = TA + 2, NRY = DIM == 3 ? BB + 2 : 1;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= tiles_x * tiles_y) return;
+    const int tx = wid / tiles_y, ty = wid - tx * tiles_y;
+    // the owned columns of this tile column pair
+    size_t colbase[TA * BB];
+    bool colok[TA * BB];
+#pragma unroll
+    for (int c = 0; c < TA * BB; ++c) {
+        const int lx = c / BB, ly = c - lx * BB;
+        const int cx = tx * TA + lx, cy = ty * BB + ly;
+        colok[c] = cx >= cx_lo && cx <= cx_hi && cx < ncx && cy < ncy;
+        colbase[c] = (size_t)(DIM == 3 ? cx * ncy + cy : cx) * nf;
+    }
+    auto C = [&](int f) {     // particles of the owned columns below fine boundary f
+        int t = 0;
+#pragma unroll
+        for (int c = 0; c < TA * BB; ++c)
+            if (colok[c]) t += cs[colbase[c] + f];
+        return t;
+    };
+    auto Sg = [&](int f) {    // particles of the staged columns below fine boundary f
+        int t = 0;
+        for (int rx = 0; rx < NRX; ++rx)
+            for (int ry = 0; ry < NRY; ++ry) {
+                const int cx = tx * TA - 1 + rx, cy = DIM == 3 ? ty * BB - 1 + ry : 0;
+                if (cx >= 0 && cx < ncx && cy >= 0 && cy < ncy) t += cs[(size_t)(DIM == 3 ? cx * ncy + cy : cx) * nf + f];
+            }
+        return t;
+    };
+    int f0 = 0;
+    int c0 = C(0);
+    const int cend = C(nf);
+    const int pad = 3 * NRX * NRY;          // alignment slack of the staged runs
+    // Two passes of the same cut (write = 0: count into off[wid]; an exclusive scan; write = 1: fill from off[wid]), so the list
+    // is in (tx, ty, f0) order: the CTAs then walk the domain like a launch in that order would, and the candidates two
+    // neighbouring tile columns share are still in L2 when the second one needs them (an unordered list reads every record
+    // ~3x from DRAM: 2.8 GB instead of 0.9 GB at 10 M particles, profiles/r2_exp_log.txt)
+    int nt = 0;
+    const int k0 = write ? off[wid] : 0;
+    while (f0 < nf && c0 < cend) {          // (c0 == cend: nothing above f0)
+        int best = f0 + 1;                  // at least one fine cell per tile (a cell denser than the target runs in several rounds)
+        const int s0 = Sg(max(f0 - sub, 0));
+        for (int off = 0; off < gfcap; off += 32) {
+            const int fe = f0 + 1 + off + lane;
+            const bool valid = fe <= nf && fe - f0 <= gfcap;
+            const int cnt = valid ? C(fe) - c0 : 0x7fffffff;
+            const int staged = valid ? Sg(min(fe + sub, nf)) - s0 + pad : 0x7fffffff;
+            const unsigned m = __ballot_sync(0xffffffffu, valid && cnt <= target && staged <= jcap);
+            if (m) best = max(best, f0 + off + 32 - __clz(m));     // counts are monotone: the set lanes form a prefix
+            if (m != 0xffffffffu) break;
+        }
+        const int cb = C(best);
+        if (cb > c0) {
+            if (write && lane == 0) tiles[k0 + nt] = make_int4(tx, ty, f0, best - f0);
+            ++nt;
+        }
+        f0 = best; c0 = cb;
+    }
+    if (!write && lane == 0) off[wid] = nt;
+}
+
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false, bool REC = false, int DBG = 0, int NBUF = 2>
+__global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, ZTile T) {
     using D = TileDims<DIM, TA, TB>;
+    using P2 = typename RecPair<R>::type;
     constexpr int NR = D::NR, NI = D::NI, RY = D::RY, BB = D::BB;
     constexpr int NW = NT / 32;
     constexpr int NRUN = DIM == 3 ? 9 : 3;
     constexpr int FAST = DIM - 1;
+    constexpr int kZJcap = zjcap<NT>(), kZRow = kZJcap + kZPad;
+    constexpr int NTAB = NR + NR + 1 + NI + NI + 1 + 4 + NW;     // per buffer: gbeg, voff, ibeg, ipre, meta (tx ty f0 gf), far flag per warp
     static_assert(NR <= 32 && NI <= 32, "one warp scans the run and column tables");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int S = g.sub, GF = T.GF, W = GF + 2 * S + 1;   // W fine-cell boundaries per staged run
-    // ---- shared memory carve-up
-    int* s_cs = reinterpret_cast<int*>(smem_raw);             // NR * W   staged offset of every fine-cell boundary
-    int* s_gbeg = s_cs + NR * W;                               // NR       global begin of each run
-    int* s_voff = s_gbeg + NR;                                 // NR + 1   staged offset of each run (multiples of 4)
-    int* s_ibeg = s_voff + NR + 1;                             // NI       global begin of each i segment
-    int* s_ipre = s_ibeg + NI;                                 // NI + 1   prefix of i counts
-    size_t off = ((size_t)(NR * W + NR + NR + 1 + NI + NI + 1) * sizeof(int) + 15) & ~(size_t)15;
-    float* s_x = reinterpret_cast<float*>(smem_raw + off);
-    float* s_y = s_x + kZRow;
-    float* s_z = s_y + kZRow;
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_z + (DIM == 3 ? kZRow : 0));   // maxw * NT
-    int* s_base = reinterpret_cast<int*>(s_mask + T.maxw * NT);                      // maxw * NT: global index of a word's first candidate
+    const int S = g.sub, WM = T.wmax;
+    // ---- shared memory carve-up: two buffers of (tables, boundary table, staged rows), then the mask words
+    const int tab_ints = (NTAB + NR * WM + 3) & ~3;
+    int* const s_tab0 = reinterpret_cast<int*>(smem_raw);
+    float* const s_row0 = reinterpret_cast<float*>(smem_raw + (size_t)NBUF * tab_ints * sizeof(int));
+    constexpr int kRows = DIM == 3 ? 3 : 2;
+    unsigned* const s_mask = reinterpret_cast<unsigned*>(s_row0 + NBUF * kRows * kZRow);   // maxw * NT
+    unsigned short* const s_base = reinterpret_cast<unsigned short*>(s_mask + T.maxw * NT);   // maxw * NT: staged run (<< 11) | staged index of a word's first candidate
+    static_assert(kZRow <= 2048 && NR <= 32, "a word's base packs the staged index in 11 bits and the run in 5");
 
-    using P2 = typename RecPair<R>::type;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- which tile
-    int b = blockIdx.x;
-    const int tf = b % T.tiles[2]; b /= T.tiles[2];
-    const int ty = DIM == 3 ? b % T.tiles[1] : 0; if (DIM == 3) b /= T.tiles[1];
-    const int tx = b;
-    const int cx0 = tx * TA, cy0 = ty * BB, f0 = tf * GF;
     const int nf = g.n[FAST];                       // fine cells along the fast axis
     const int ncx = g.n[0], ncy = DIM == 3 ? g.n[1] : 1;
+    const int ntiles = *T.ntiles;
+    const R cellR = g.cell;
+    const float cellf = (float)g.cell;
+    const float inv_cf = (float)S / cellf;          // 1 / fine cell edge
+    const int MAXW = T.maxw;
+    unsigned* const my_mask = s_mask + tid;
+    unsigned short* const my_base = s_base + tid;
 
-    // ---- fine-cell boundaries of every staged run (global indices first)
-    for (int t = tid; t < NR * W; t += NT) {
-        const int q = t / W, tt = t - q * W;
-        const int rx = q / RY, ry = q - rx * RY;
-        const int cx = cx0 - 1 + rx, cy = DIM == 3 ? cy0 - 1 + ry : 0;
-        int gi = 0;   // column outside the grid: all boundaries equal -> empty run
-        if (cx >= 0 && cx < ncx && cy >= 0 && cy < ncy) {
-            const int col = DIM == 3 ? cx * ncy + cy : cx;
-            gi = A.cell_start[(size_t)col * nf + min(max(f0 - S + tt, 0), nf)];
+    // ---- stage tile k into buffer b: every warp derives the run table itself (two look-ups per lane + a shuffle scan),
+    // then copies its own runs (boundaries + candidates).  No block-wide barrier inside.
+    auto stage_tile = [&](int k, int b) {
+        int* const tab = s_tab0 + b * tab_ints;
+        int* const s_gbeg = tab; int* const s_voff = s_gbeg + NR; int* const s_ibeg = s_voff + NR + 1; int* const s_ipre = s_ibeg + NI;
+        int* const s_meta = s_ipre + NI + 1; int* const s_far = s_meta + 4; int* const s_cs = s_far + NW;
+        float* const s_x = s_row0 + b * kRows * kZRow;
+        const int4 t = T.tiles[k];
+        const int cx0 = t.x * TA, cy0 = t.y * BB, f0 = t.z, gf = t.w, W = gf + 2 * S + 1;
+        // run extents (lane q < NR)
+        int gb = 0, len = 0;
+        long long colq = 0;
+        bool okq = false;
+        if (lane < NR) {
+            const int rx = lane / RY, ry = lane - rx * RY;
+            const int cx = cx0 - 1 + rx, cy = DIM == 3 ? cy0 - 1 + ry : 0;
+            okq = cx >= 0 && cx < ncx && cy >= 0 && cy < ncy;
+            colq = (long long)(DIM == 3 ? cx * ncy + cy : cx) * nf;
+            if (okq) { gb = A.cell_start[colq + max(f0 - S, 0)]; len = A.cell_start[colq + min(f0 + gf + S, nf)] - gb; }
         }
-        s_cs[t] = gi;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // staged offsets: exclusive scan of the run lengths rounded up to 4 (so every run starts 16-byte aligned)
-        int len = 0, gb = 0;
-        if (lane < NR) { gb = s_cs[lane * W]; len = s_cs[lane * W + W - 1] - gb; }
-        int incl = (len + 3) & ~3;
+        const int alen = (len + 3) & ~3;            // every run starts 16-byte aligned in the staged rows
+        int incl = alen;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += y;
         }
-        if (lane < NR) { s_gbeg[lane] = gb; s_voff[lane] = incl - ((len + 3) & ~3); }
-        if (lane == NR - 1) s_voff[NR] = incl;
-        // i segments: tile columns, fine cells [f0, f0 + GF) == boundaries tt = S .. S + GF of the centre runs
-        int cnt = 0, beg = 0;
-        if (lane < NI) {
-            const int lx = lane / BB, ly = lane - lx * BB;
-            const int q = (lx + 1) * RY + (DIM == 3 ? ly + 1 : 0);
-            const int cx = cx0 + lx, cy = cy0 + ly;
-            if (cx >= g.cx_lo && cx <= g.cx_hi && cy < ncy) { beg = s_cs[q * W + S]; cnt = s_cs[q * W + S + GF] - beg; }   // ghost layers are never i
-        }
-        int ipre = cnt;
+        const int voff = incl - alen;
+        const int M = __shfl_sync(0xffffffffu, incl, NR - 1);
+        const bool dense = M > min(kZJcap, T.jcap);
+        if (warp == 0) {
+            if (lane < NR) { s_gbeg[lane] = gb - voff; s_voff[lane] = voff; }      // s_gbeg: global index minus staged index of the run
+            if (lane == NR - 1) s_voff[NR] = M;
+            // i segments: the tile's own columns, fine cells [f0, f0 + gf)
+            int cnt = 0, beg = 0;
+            if (lane < NI) {
+                const int lx = lane / BB, ly = lane - lx * BB;
+                const int cx = cx0 + lx, cy = cy0 + ly;
+                if (cx >= g.cx_lo && cx <= g.cx_hi && cx < ncx && cy < ncy) {       // ghost layers are never i
+                    const long long col = (long long)(DIM == 3 ? cx * ncy + cy : cx) * nf;
+                    beg = A.cell_start[col + f0]; cnt = A.cell_start[col + f0 + gf] - beg;
+                }
+            }
+            int ipre = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, ipre, d);
-            if (lane >= d) ipre += y;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, ipre, d);
+                if (lane >= d) ipre += y;
+            }
+            if (lane < NI) { s_ibeg[lane] = beg; s_ipre[lane] = ipre - cnt; }
+            if (lane == NI - 1) s_ipre[NI] = ipre;
+            if (lane == 0) { s_meta[0] = t.x; s_meta[1] = t.y; s_meta[2] = f0; s_meta[3] = dense ? -gf : gf; }
         }
-        if (lane < NI) { s_ibeg[lane] = beg; s_ipre[lane] = ipre - cnt; }
-        if (lane == NI - 1) s_ipre[NI] = ipre;
-    }
-    __syncthreads();
-    const int ni = s_ipre[NI];
-    if (ni == 0) return;                      // empty tile (uniform exit)
-    const int M = s_voff[NR];
-    // tile-local coordinates: origin = low corner of the tile's own cells (no global load needed)
-    const R cellR = g.cell;
-    const R ox = g.lo[0] + (R)cx0 * cellR;
-    const R oy = DIM == 3 ? g.lo[1] + (R)cy0 * cellR : g.lo[1] + (R)f0 * (cellR / (R)S);
-    const R oz = DIM == 3 ? g.lo[2] + (R)f0 * (cellR / (R)S) : (R)0;
-    bool far = false;
-    const bool dense = M > min(kZJcap, T.jcap);
-    if (!dense) {
-        // ---- rebase boundaries to staged offsets (every entry by the thread that owns it; the run tables are read-only by now)
-        for (int t = tid; t < NR * W; t += NT) {
-            const int q = t / W;
-            s_cs[t] = s_voff[q] + (s_cs[t] - s_gbeg[q]);
-        }
-    }
-    __syncthreads();
-    if (!dense) {
-        // ---- stage candidates: one warp per run, coalesced; the slack up to the next multiple of 4 holds a far-away dummy
-        const float far_lim = (float)(GF / S + 6) * (float)g.cell;
-        for (int q = warp; q < NR; q += NW) {
-            const int gb = s_gbeg[q], vo = s_voff[q], plen = s_voff[q + 1] - vo;
-            const int len = s_cs[q * W + W - 1] - vo;      // true length (rebased boundaries)
-            for (int v = lane; v < plen; v += 32) {
-                float px = 1e30f, py = 0.0f, pz = 0.0f;    // dummy: never within any cutoff
-                if (v < len) {
-                    const int gj = gb + v;
-                    px = (float)(A.x[gj] - ox); py = (float)(A.y[gj] - oy); pz = DIM == 3 ? (float)(A.z[gj] - oz) : 0.0f;
-                    far |= !(fabsf(px) <= far_lim && fabsf(py) <= far_lim && fabsf(pz) <= far_lim);
+        bool far = false;
+        if (!dense) {
+            // tile-local coordinates: origin = low corner of the tile's own cells (no global load needed)
+            const R ox = g.lo[0] + (R)cx0 * cellR;
+            const R oy = DIM == 3 ? g.lo[1] + (R)cy0 * cellR : g.lo[1] + (R)f0 * (cellR / (R)S);
+            const R oz = DIM == 3 ? g.lo[2] + (R)f0 * (cellR / (R)S) : (R)0;
+            const float far_lim = (float)(gf / S + 6) * cellf;
+            for (int q = warp; q < NR; q += NW) {
+                const int gbq = __shfl_sync(0xffffffffu, gb, q), vo = __shfl_sync(0xffffffffu, voff, q);
+                const int lenq = __shfl_sync(0xffffffffu, len, q), plen = __shfl_sync(0xffffffffu, alen, q);
+                const bool ok = __shfl_sync(0xffffffffu, (int)okq, q) != 0;
+                const long long col = __shfl_sync(0xffffffffu, colq, q);
+                // staged offset of every fine-cell boundary of the run
+                for (int tt = lane; tt < W; tt += 32)
+                    s_cs[q * WM + tt] = vo + (ok ? A.cell_start[col + min(max(f0 - S + tt, 0), nf)] - gbq : 0);
+                // candidates, coalesced; the slack up to the next multiple of 4 holds a far-away dummy
+                for (int v = lane; v < plen; v += 32) {
+                    float px = 1e30f, py = 0.0f, pz = 0.0f;    // dummy: never within any cutoff
+                    if (v < lenq) {
+                        const int gj = gbq + v;
+                        px = (float)(A.x[gj] - ox); py = (float)(A.y[gj] - oy); pz = DIM == 3 ? (float)(A.z[gj] - oz) : 0.0f;
+                        far |= !(fabsf(px) <= far_lim && fabsf(py) <= far_lim && fabsf(pz) <= far_lim);
+                    }
+                    s_x[vo + v] = px; s_x[kZRow + vo + v] = py; if (DIM == 3) s_x[2 * kZRow + vo + v] = pz;
                 }
-                s_x[vo + v] = px; s_y[vo + v] = py; if (DIM == 3) s_z[vo + v] = pz;
             }
+            if (warp == NW - 1)
+                for (int v = lane; v < kZPad; v += 32) { s_x[M + v] = 1e30f; s_x[kZRow + M + v] = 0.0f; if (DIM == 3) s_x[2 * kZRow + M + v] = 0.0f; }
         }
-        for (int v = tid; v < kZPad; v += NT) { s_x[M + v] = 1e30f; s_y[M + v] = 0.0f; if (DIM == 3) s_z[M + v] = 0.0f; }
-    }
-    far = __syncthreads_or(far);
-    if (dense || far) {
-        // tile denser than the staging buffer, or holding particles far outside the box (clamped into its cells): the exact
-        // per-particle gather for its particles
-        for (int ii = tid; ii < ni; ii += NT) {
-            int c = 0;
-            while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
-            gather_one<R, DIM, false, CONT, MOM, COUPLED>(g, C, A, s_ibeg[c] + (ii - s_ipre[c]));
+        far = __any_sync(0xffffffffu, far);
+        if (lane == 0) s_far[warp] = far;
+    };
+
+    // ---- evaluate the staged tile of buffer b
+    auto compute_tile = [&](int b) {
+        const int* const tab = s_tab0 + b * tab_ints;
+        const int* const s_gbeg = tab; const int* const s_voff = s_gbeg + NR; const int* const s_ibeg = s_voff + NR + 1; const int* const s_ipre = s_ibeg + NI;
+        const int* const s_meta = s_ipre + NI + 1; const int* const s_far = s_meta + 4; const int* const s_cs = s_far + NW;
+        const float* const s_x = s_row0 + b * kRows * kZRow;
+        const int ni = s_ipre[NI];
+        if (ni == 0) return;
+        const int cx0 = s_meta[0] * TA, cy0 = s_meta[1] * BB, f0 = s_meta[2];
+        bool fallback = s_meta[3] < 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) fallback |= s_far[w] != 0;
+        if (fallback) {
+            // tile denser than the staging buffer, or holding particles far outside the box (clamped into its cells): the exact
+            // per-particle gather for its particles
+            for (int ii = tid; ii < ni; ii += NT) {
+                int c = 0;
+                while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
+                gather_one<R, DIM, false, CONT, MOM, COUPLED>(g, C, A, s_ibeg[c] + (ii - s_ipre[c]));
+            }
+            return;
         }
-        return;
-    }
-
-    const int MAXW = T.maxw;
-    const float cellf = (float)g.cell;
-    const float inv_cf = (float)S / cellf;          // 1 / fine cell edge
-    unsigned* const my_mask = s_mask + tid;
-    int* const my_base = s_base + tid;
-    for (int ii0 = warp * 32; ii0 < ni; ii0 += NT) {   // a warp takes 32 consecutive particles per round (warp-uniform trip count)
-        const int ii = ii0 + lane;
-        const bool active = ii < ni;
-        int c = 0, gi = 0, lx = 0, ly = 0;
-        IState<R, DIM> I;
-        Acc<R> a{0, 0, 0, 0}, a2{0, 0, 0, 0};
-        float xf = 0, yf = 0, zf = 0, rc2f = 0, rc2m = -1.0f;
-        bool fluid_i = true;
-        if (active) {
-            while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
-            gi = s_ibeg[c] + (ii - s_ipre[c]);
-            lx = c / BB; ly = c - lx * BB;
-            if (REC) {
-                const P2* q = reinterpret_cast<const P2*>(A.rec) + rec_index(gi);
-                const P2 r0 = q[0], r1 = q[8], r2 = q[16], r3 = q[24], r4 = q[32];
-                if (COUPLED) fluid_i = r4.x > (R)0;
-                load_i<R, DIM>(I, C, r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, r4.y);
-            } else {
-                if (COUPLED) fluid_i = A.m[gi] > (R)0;
-                load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
-                               A.por2[gi], A.h[gi]);
+        const int gf = s_meta[3], W = gf + 2 * S + 1;
+        const R ox = g.lo[0] + (R)cx0 * cellR;
+        const R oy = DIM == 3 ? g.lo[1] + (R)cy0 * cellR : g.lo[1] + (R)f0 * (cellR / (R)S);
+        const R oz = DIM == 3 ? g.lo[2] + (R)f0 * (cellR / (R)S) : (R)0;
+        for (int ii0 = warp * 32; ii0 < ni; ii0 += NT) {   // a warp takes 32 consecutive particles per round (warp-uniform trip count)
+            const int ii = ii0 + lane;
+            const bool active = ii < ni;
+            int c = 0, gi = 0, lx = 0, ly = 0;
+            IState<R, DIM> I;
+            Acc<R> a{0, 0, 0, 0}, a2{0, 0, 0, 0};
+            float xf = 0, yf = 0, zf = 0, rc2f = 0, rc2m = -1.0f;
+            bool fluid_i = true;
+            if (active) {
+                while (c + 1 < NI && ii >= s_ipre[c + 1]) ++c;
+                gi = s_ibeg[c] + (ii - s_ipre[c]);
+                lx = c / BB; ly = c - lx * BB;
+                if (REC) {
+                    const P2* q = reinterpret_cast<const P2*>(A.rec) + rec_index(gi);
+                    const P2 r0 = q[0], r1 = q[8], r2 = q[16], r3 = q[24], r4 = q[32];
+                    if (COUPLED) fluid_i = r4.x > (R)0;
+                    load_i<R, DIM>(I, C, r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y, r4.y);
+                } else {
+                    if (COUPLED) fluid_i = A.m[gi] > (R)0;
+                    load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
+                                   A.por2[gi], A.h[gi]);
+                }
+                xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
+                // conservative f32 pre-filter: relative margin 2^-15 on rc^2 (>> the f32 error of tile-local coordinates, see
+                // launch_zrun); the range cull below uses twice that
+                rc2f = __double2float_ru((double)(UNI ? C.u_rc2 : I.rc2) * (1.0 + 1.0 / 32768.0));
+                rc2m = rc2f * (1.0f + 1.0f / 16384.0f);
             }
-            xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
-            // conservative f32 pre-filter: relative margin 2^-15 on rc^2 (>> the f32 error of tile-local coordinates, see
-            // launch_zrun); the range cull below uses twice that
-            rc2f = __double2float_ru((double)(UNI ? C.u_rc2 : I.rc2) * (1.0 + 1.0 / 32768.0));
-            rc2m = rc2f * (1.0f + 1.0f / 16384.0f);
-        }
-        const float fz = DIM == 3 ? zf : yf;            // coordinate along the fast axis, relative to fine cell f0
-        const float2 xf2 = make_float2(xf, xf), yf2 = make_float2(yf, yf), zf2 = make_float2(zf, zf);
-        const float2 nrc2 = make_float2(-rc2f, -rc2f);
+            const float fz = DIM == 3 ? zf : yf;            // coordinate along the fast axis, relative to fine cell f0
+            const float2 xf2 = make_float2(xf, xf), yf2 = make_float2(yf, yf), zf2 = make_float2(zf, zf);
+            const float2 nrc2 = make_float2(-rc2f, -rc2f);
 
-        // ---- per-lane scan range of stencil run k: staged [vs, ve), aligned start a4 = vs & ~3, ng 4-groups
-        int q_run = 0, vs = 0, ve = 0;
-        auto open_run = [&](int k) {
-            const int ax = DIM == 3 ? k / 3 : k, ay = DIM == 3 ? k - ax * 3 : 0;
-            q_run = (lx + ax) * RY + (DIM == 3 ? ly + ay : 0);
-            // distance from the particle to the footprint of that column (0 for its own column)
-            float dxc = 0.0f, dyc = 0.0f;
-            if (ax == 0) dxc = fmaxf(xf - (float)lx * cellf, 0.0f);
-            if (ax == 2) dxc = fmaxf((float)(lx + 1) * cellf - xf, 0.0f);
-            if (DIM == 3) {
-                if (ay == 0) dyc = fmaxf(yf - (float)ly * cellf, 0.0f);
-                if (ay == 2) dyc = fmaxf((float)(ly + 1) * cellf - yf, 0.0f);
-            }
-            const float rem = rc2m - (dxc * dxc + dyc * dyc);
-            vs = ve = 0;
-            if (active && rem > 0.0f) {
-                const float zext = sqrtf(rem) * 1.00001f;
-                // fine cells [tlo, thi] relative to boundary 0 of the staged run (= fine cell f0 - S); +-1e-3 cell of slack,
-                // then clamped like the keys themselves (particles outside the box sit in the edge cells)
-                int flo = (int)floorf((fz - zext) * inv_cf - 1e-3f) + f0, fhi = (int)floorf((fz + zext) * inv_cf + 1e-3f) + f0;
-                flo = min(max(flo, 0), nf - 1); fhi = min(max(fhi, 0), nf - 1);
-                const int tlo = min(max(flo - (f0 - S), 0), W - 2), thi = min(max(fhi - (f0 - S), 0), W - 2);
-                vs = s_cs[q_run * W + tlo];
-                ve = s_cs[q_run * W + thi + 1];
-            }
-        };
+            // ---- per-lane scan range of stencil run k: staged [vs, ve), aligned start a4 = vs & ~3, ng 4-groups
+            int q_run = 0, vs = 0, ve = 0;
+            auto open_run = [&](int k) {
+                const int ax = DIM == 3 ? k / 3 : k, ay = DIM == 3 ? k - ax * 3 : 0;
+                q_run = (lx + ax) * RY + (DIM == 3 ? ly + ay : 0);
+                // distance from the particle to the footprint of that column (0 for its own column)
+                float dxc = 0.0f, dyc = 0.0f;
+                if (ax == 0) dxc = fmaxf(xf - (float)lx * cellf, 0.0f);
+                if (ax == 2) dxc = fmaxf((float)(lx + 1) * cellf - xf, 0.0f);
+                if (DIM == 3) {
+                    if (ay == 0) dyc = fmaxf(yf - (float)ly * cellf, 0.0f);
+                    if (ay == 2) dyc = fmaxf((float)(ly + 1) * cellf - yf, 0.0f);
+                }
+                const float rem = rc2m - (dxc * dxc + dyc * dyc);
+                vs = ve = 0;
+                if (active && rem > 0.0f) {
+                    const float zext = sqrtf(rem) * 1.00001f;
+                    // fine cells [tlo, thi] relative to boundary 0 of the staged run (= fine cell f0 - S); +-1e-3 cell of slack,
+                    // then clamped like the keys themselves (particles outside the box sit in the edge cells)
+                    int flo = (int)floorf((fz - zext) * inv_cf - 1e-3f) + f0, fhi = (int)floorf((fz + zext) * inv_cf + 1e-3f) + f0;
+                    flo = min(max(flo, 0), nf - 1); fhi = min(max(fhi, 0), nf - 1);
+                    const int tlo = min(max(flo - (f0 - S), 0), W - 2), thi = min(max(fhi - (f0 - S), 0), W - 2);
+                    vs = s_cs[q_run * WM + tlo];
+                    ve = s_cs[q_run * WM + thi + 1];
+                }
+            };
 
-        int k = 0, wc = 0;          // warp-uniform scan cursor: stencil run, 32-candidate chunk inside it
-        while (true) {
-            // ---- phase 1: pre-filter on staged f32 coordinates -> bit masks (bit 31 = first candidate of the word)
-            int nw = 0, nch = 0;
-            while (k < NRUN) {
-                open_run(k);
-                int a4 = vs & ~3;
-                const int ng = (ve - a4 + 3) >> 2;
-                const int Tg = __reduce_max_sync(0xffffffffu, ve > vs ? ng : 0);   // the warp scans its longest range
-                bool full = false;
-                while (wc * 8 < Tg) {
-                    if (nch == MAXW) { full = true; break; }
-                    const int iters = min(8, Tg - wc * 8);
-                    const int j0 = a4 + wc * 32;
-                    const float* px = s_x + min(j0, kZRow - 32);           // (only a lane past its own range is ever clamped)
-                    unsigned m = 0;
+            int k = 0, wc = 0;          // warp-uniform scan cursor: stencil run, 32-candidate chunk inside it
+            while (true) {
+                // ---- phase 1: pre-filter on staged f32 coordinates -> bit masks (bit 31 = first candidate of the word)
+                int nw = 0;
+                while (k < NRUN) {
+                    open_run(k);
+                    const int a4 = vs & ~3;
+                    const int ng = (ve - a4 + 3) >> 2;
+                    const int Tg = __reduce_max_sync(0xffffffffu, ve > vs ? ng : 0);   // the warp scans its longest range
+                    bool full = false;
+                    while (wc * 8 < Tg) {
+                        if (__any_sync(0xffffffffu, nw == MAXW)) { full = true; break; }
+                        const int iters = min(8, Tg - wc * 8);
+                        const int j0 = a4 + wc * 32;
+                        const float* px = s_x + min(j0, kZRow - 32);           // (only a lane past its own range is ever clamped)
+                        unsigned m = 0;
 #pragma unroll 4
-                    for (int it = 0; it < iters; ++it, px += 4) {
-                        const float4 X = *reinterpret_cast<const float4*>(px), Y = *reinterpret_cast<const float4*>(px + kZRow);
-                        const float4 Z = DIM == 3 ? *reinterpret_cast<const float4*>(px + 2 * kZRow) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        const float2 dxa = __fadd2_rn(xf2, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(xf2, make_float2(-X.z, -X.w));
-                        const float2 dya = __fadd2_rn(yf2, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(yf2, make_float2(-Y.z, -Y.w));
-                        float2 da = __ffma2_rn(dya, dya, __ffma2_rn(dxa, dxa, nrc2));
-                        float2 db = __ffma2_rn(dyb, dyb, __ffma2_rn(dxb, dxb, nrc2));
-                        if (DIM == 3) {
-                            const float2 dza = __fadd2_rn(zf2, make_float2(-Z.x, -Z.y)), dzb = __fadd2_rn(zf2, make_float2(-Z.z, -Z.w));
-                            da = __ffma2_rn(dza, dza, da);
-                            db = __ffma2_rn(dzb, dzb, db);
+                        for (int it = 0; it < iters; ++it, px += 4) {
+                            const float4 X = *reinterpret_cast<const float4*>(px), Y = *reinterpret_cast<const float4*>(px + kZRow);
+                            const float4 Z = DIM == 3 ? *reinterpret_cast<const float4*>(px + 2 * kZRow) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            const float2 dxa = __fadd2_rn(xf2, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(xf2, make_float2(-X.z, -X.w));
+                            const float2 dya = __fadd2_rn(yf2, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(yf2, make_float2(-Y.z, -Y.w));
+                            float2 da = __ffma2_rn(dya, dya, __ffma2_rn(dxa, dxa, nrc2));
+                            float2 db = __ffma2_rn(dyb, dyb, __ffma2_rn(dxb, dxb, nrc2));
+                            if (DIM == 3) {
+                                const float2 dza = __fadd2_rn(zf2, make_float2(-Z.x, -Z.y)), dzb = __fadd2_rn(zf2, make_float2(-Z.z, -Z.w));
+                                da = __ffma2_rn(dza, dza, da);
+                                db = __ffma2_rn(dzb, dzb, db);
+                            }
+                            // sign bit of d = r^2 - rc^2 -> the word (d < 0: inside the margin-inflated cutoff)
+                            m = __funnelshift_l(__float_as_uint(da.x), m, 1);
+                            m = __funnelshift_l(__float_as_uint(da.y), m, 1);
+                            m = __funnelshift_l(__float_as_uint(db.x), m, 1);
+                            m = __funnelshift_l(__float_as_uint(db.y), m, 1);
                         }
-                        // sign bit of d = r^2 - rc^2 -> the word (d < 0: inside the margin-inflated cutoff)
-                        m = __funnelshift_l(__float_as_uint(da.x), m, 1);
-                        m = __funnelshift_l(__float_as_uint(da.y), m, 1);
-                        m = __funnelshift_l(__float_as_uint(db.x), m, 1);
-                        m = __funnelshift_l(__float_as_uint(db.y), m, 1);
+                        m <<= 32 - 4 * iters;                                  // left-align: bit 31 = candidate j0
+                        const int lim = min(max(ve - j0, 0), 32);              // this lane's own range ends here; beyond it: over-scan with the warp
+                        m &= (unsigned)(0xFFFFFFFF00000000ull >> lim);
+                        if (wc == 0) m &= 0xFFFFFFFFu >> (vs - a4);            // aligned-down head
+                        if (m) {
+                            my_mask[nw * NT] = m;
+                            my_base[nw * NT] = (unsigned short)((q_run << 11) | j0);
+                            ++nw;
+                        }
+                        ++wc;
                     }
-                    m <<= 32 - 4 * iters;                                  // left-align: bit 31 = candidate j0
-                    const int lim = min(max(ve - j0, 0), 32);              // this lane's own range ends here; beyond it: over-scan with the warp
-                    m &= (unsigned)(0xFFFFFFFF00000000ull >> lim);
-                    if (wc == 0) m &= 0xFFFFFFFFu >> (vs - a4);            // aligned-down head
-                    if (m) {
-                        my_mask[nw * NT] = m;
-                        my_base[nw * NT] = j0 + (s_gbeg[q_run] - s_voff[q_run]);
-                        ++nw;
-                    }
-                    ++nch;
-                    ++wc;
+                    if (full) break;
+                    ++k; wc = 0;
                 }
-                if (full) break;
-                ++k; wc = 0;
-            }
-            // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
-            {
-                // hit iterator over the mask words (none of them empty): m = bits left in the current word, base31 = global index
-                // of its first candidate + 31, w = next word
-                int w = 0, base31 = 0;
-                unsigned m = 0;
-                if (nw > 0 && DBG != 3) { m = my_mask[0]; base31 = my_base[0] + 31; w = 1; }
-                if (DBG == 3) a.au += (R)nw;      // timing ablation: phase 1 only
-                auto pop = [&]() -> int {      // requires m != 0
-                    const int msb = 31 - __clz(m);
-                    int j = base31 - msb;
-                    asm("" : "+r"(j));        // keep j a plain 32-bit value: the record index below is 32-bit arithmetic + one IMAD.WIDE
-                    m ^= 1u << msb;
-                    if (m == 0 && w < nw) { m = my_mask[w * NT]; base31 = my_base[w * NT] + 31; ++w; }
-                    return j;
-                };
-                while (m != 0) {
-                    const int j0 = pop();
-                    const bool v1 = m != 0;
-                    const int j1 = v1 ? pop() : j0;
-                    R xj0, yj0, zj0, uj0, vj0, wj0, rj0, pj0, xj1, yj1, zj1, uj1, vj1, wj1, rj1, pj1, mj0 = A.m_uni, mj1 = A.m_uni;
-                    const R rc2 = UNI ? C.u_rc2 : I.rc2;
-                    if (DBG == 1) {     // timing ablation (wrong results): no gathers, the j state is made up from the index
-                        xj0 = I.x + (R)(j0 & 15) * (R)1e-3; yj0 = I.y + (R)(j0 & 7) * (R)1e-3; zj0 = I.z; uj0 = I.u; vj0 = I.v; wj0 = (R)j0; rj0 = I.rho; pj0 = I.por2;
-                        xj1 = I.x + (R)(j1 & 15) * (R)1e-3; yj1 = I.y + (R)(j1 & 7) * (R)1e-3; zj1 = I.z; uj1 = I.u; vj1 = I.v; wj1 = (R)j1; rj1 = I.rho; pj1 = I.por2;
-                    } else if (REC) {
-                        const P2* q0 = reinterpret_cast<const P2*>(A.rec) + rec_index(j0);
-                        const P2* q1 = reinterpret_cast<const P2*>(A.rec) + rec_index(j1);
-                        const P2 a0 = q0[0], b0 = q0[8], a1 = q1[0], b1 = q1[8];
-                        P2 c0, d0, c1, d1;
-                        if (DBG == 4) { c0.x = I.v; c0.y = I.w; d0.x = I.rho; d0.y = I.por2; c1 = c0; d1 = d0; }   // timing ablation: half the gather
-                        else { c0 = q0[16]; d0 = q0[24]; c1 = q1[16]; d1 = q1[24]; }
-                        xj0 = a0.x; yj0 = a0.y; zj0 = b0.x; uj0 = b0.y; vj0 = c0.x; wj0 = c0.y; rj0 = d0.x; pj0 = d0.y;
-                        xj1 = a1.x; yj1 = a1.y; zj1 = b1.x; uj1 = b1.y; vj1 = c1.x; wj1 = c1.y; rj1 = d1.x; pj1 = d1.y;
-                        if (!UNI) { mj0 = q0[32].x; mj1 = q1[32].x; }
-                    } else {
-                        xj0 = A.x[j0]; yj0 = A.y[j0]; zj0 = DIM == 3 ? A.z[j0] : (R)0; uj0 = A.u[j0]; vj0 = A.v[j0]; wj0 = DIM == 3 ? A.w[j0] : (R)0;
-                        rj0 = A.rho[j0]; pj0 = A.por2[j0];
-                        xj1 = A.x[j1]; yj1 = A.y[j1]; zj1 = DIM == 3 ? A.z[j1] : (R)0; uj1 = A.u[j1]; vj1 = A.v[j1]; wj1 = DIM == 3 ? A.w[j1] : (R)0;
-                        rj1 = A.rho[j1]; pj1 = A.por2[j1];
-                        if (!UNI) { mj0 = A.m[j0]; mj1 = A.m[j1]; }
+                // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
+                {
+                    // hit iterator over the mask words (none of them empty): m = bits left in the current word, base31 = global index
+                    // of its first candidate + 31, w = next word
+                    int w = 0, base31 = 0;
+                    unsigned m = 0;
+                    auto word_base = [&](int ww) { const int b16 = my_base[ww * NT]; return (b16 & 2047) + s_gbeg[b16 >> 11] + 31; };
+                    if (nw > 0 && DBG != 3) { m = my_mask[0]; base31 = word_base(0); w = 1; }
+                    if (DBG == 3) a.au += (R)nw;      // timing ablation: phase 1 only
+                    auto pop = [&]() -> int {      // requires m != 0
+                        const int msb = 31 - __clz(m);
+                        int j = base31 - msb;
+                        asm("" : "+r"(j));        // keep j a plain 32-bit value: the record index below is 32-bit arithmetic + one IMAD.WIDE
+                        m ^= 1u << msb;
+                        if (m == 0 && w < nw) { m = my_mask[w * NT]; base31 = word_base(w); ++w; }
+                        return j;
+                    };
+                    while (m != 0) {
+                        const int j0 = pop();
+                        const bool v1 = m != 0;
+                        const int j1 = v1 ? pop() : j0;
+                        R xj0, yj0, zj0, uj0, vj0, wj0, rj0, pj0, xj1, yj1, zj1, uj1, vj1, wj1, rj1, pj1, mj0 = A.m_uni, mj1 = A.m_uni;
+                        const R rc2 = UNI ? C.u_rc2 : I.rc2;
+                        if (DBG == 1) {     // timing ablation (wrong results): no gathers, the j state is made up from the index
+                            xj0 = I.x + (R)(j0 & 15) * (R)1e-3; yj0 = I.y + (R)(j0 & 7) * (R)1e-3; zj0 = I.z; uj0 = I.u; vj0 = I.v; wj0 = (R)j0; rj0 = I.rho; pj0 = I.por2;
+                            xj1 = I.x + (R)(j1 & 15) * (R)1e-3; yj1 = I.y + (R)(j1 & 7) * (R)1e-3; zj1 = I.z; uj1 = I.u; vj1 = I.v; wj1 = (R)j1; rj1 = I.rho; pj1 = I.por2;
+                        } else if (REC) {
+                            const P2* q0 = reinterpret_cast<const P2*>(A.rec) + rec_index(j0);
+                            const P2* q1 = reinterpret_cast<const P2*>(A.rec) + rec_index(j1);
+                            const P2 a0 = q0[0], b0 = q0[8], c0 = q0[16], d0 = q0[24], a1 = q1[0], b1 = q1[8], c1 = q1[16], d1 = q1[24];
+                            xj0 = a0.x; yj0 = a0.y; zj0 = b0.x; uj0 = b0.y; vj0 = c0.x; wj0 = c0.y; rj0 = d0.x; pj0 = d0.y;
+                            xj1 = a1.x; yj1 = a1.y; zj1 = b1.x; uj1 = b1.y; vj1 = c1.x; wj1 = c1.y; rj1 = d1.x; pj1 = d1.y;
+                            if (!UNI) { mj0 = q0[32].x; mj1 = q1[32].x; }
+                        } else {
+                            xj0 = A.x[j0]; yj0 = A.y[j0]; zj0 = DIM == 3 ? A.z[j0] : (R)0; uj0 = A.u[j0]; vj0 = A.v[j0]; wj0 = DIM == 3 ? A.w[j0] : (R)0;
+                            rj0 = A.rho[j0]; pj0 = A.por2[j0];
+                            xj1 = A.x[j1]; yj1 = A.y[j1]; zj1 = DIM == 3 ? A.z[j1] : (R)0; uj1 = A.u[j1]; vj1 = A.v[j1]; wj1 = DIM == 3 ? A.w[j1] : (R)0;
+                            rj1 = A.rho[j1]; pj1 = A.por2[j1];
+                            if (!UNI) { mj0 = A.m[j0]; mj1 = A.m[j1]; }
+                        }
+                        if (DBG == 2) {     // timing ablation (wrong results): gathers only, no pair body
+                            a.au += xj0 + yj0 + zj0 + uj0; a.av += vj0 + wj0 + rj0 + pj0; a2.au += xj1 + yj1 + zj1 + uj1; a2.av += vj1 + wj1 + rj1 + pj1;
+                            continue;
+                        }
+                        const R dx0 = I.x - xj0, dy0 = I.y - yj0, dz0 = DIM == 3 ? I.z - zj0 : (R)0;
+                        const R dx1 = I.x - xj1, dy1 = I.y - yj1, dz1 = DIM == 3 ? I.z - zj1 : (R)0;
+                        R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
+                        const bool in0 = r20 < rc2 && r20 > (R)0;              // the exact test (the set is defined here)
+                        const bool in1 = v1 && r21 < rc2 && r21 > (R)0;
+                        r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
+                        R m0 = in0 ? mj0 : (R)0, m1 = in1 ? mj1 : (R)0;
+                        if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
+                            m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
+                            m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
+                        }
+                        pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx0, dy0, dz0, r20, uj0, vj0, wj0, rj0, m0, pj0, a);
+                        pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx1, dy1, dz1, r21, uj1, vj1, wj1, rj1, m1, pj1, a2);
                     }
-                    if (DBG == 2) {     // timing ablation (wrong results): gathers only, no pair body
-                        a.au += xj0 + yj0 + zj0 + uj0; a.av += vj0 + wj0 + rj0 + pj0; a2.au += xj1 + yj1 + zj1 + uj1; a2.av += vj1 + wj1 + rj1 + pj1;
-                        continue;
-                    }
-                    const R dx0 = I.x - xj0, dy0 = I.y - yj0, dz0 = DIM == 3 ? I.z - zj0 : (R)0;
-                    const R dx1 = I.x - xj1, dy1 = I.y - yj1, dz1 = DIM == 3 ? I.z - zj1 : (R)0;
-                    R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
-                    const bool in0 = r20 < rc2 && r20 > (R)0;              // the exact test (the set is defined here)
-                    const bool in1 = v1 && r21 < rc2 && r21 > (R)0;
-                    r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
-                    R m0 = in0 ? mj0 : (R)0, m1 = in1 ? mj1 : (R)0;
-                    if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
-                        m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
-                        m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
-                    }
-                    pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx0, dy0, dz0, r20, uj0, vj0, wj0, rj0, m0, pj0, a);
-                    pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx1, dy1, dz1, r21, uj1, vj1, wj1, rj1, m1, pj1, a2);
                 }
+                if (k == NRUN) break;      // warp-uniform
             }
-            if (k == NRUN) break;      // warp-uniform
+            if (active) {
+                a.au += a2.au; a.av += a2.av; a.aw += a2.aw; a.arho += a2.arho;
+                store_acc<R, DIM, CONT, MOM>(A, C, gi, a);
+            }
         }
-        if (active) {
-            a.au += a2.au; a.av += a2.av; a.aw += a2.aw; a.arho += a2.arho;
-            store_acc<R, DIM, CONT, MOM>(A, C, gi, a);
-        }
+    };
+
+    // ---- persistent loop over this CTA's tiles, staging one tile ahead
+    // tiles are handed out dynamically (one atomic per tile, fetched two iterations ahead by thread 0 and published through
+    // shared memory at the barrier in between): neighbours in the list are evaluated at about the same time by different SMs
+    // (their common candidates meet in L2) and no CTA waits for a slow one at the end
+    __shared__ int s_next[2];
+    int k = blockIdx.x, k1 = blockIdx.x + gridDim.x;        // the first two tiles are static
+    if (k >= ntiles) return;
+    stage_tile(k, 0);
+    __syncthreads();
+    for (int n = 0; k < ntiles; ++n) {
+        if (tid == 0) s_next[n & 1] = atomicAdd(T.next, 1);  // tile of iteration n + 2
+        compute_tile(NBUF == 2 ? n & 1 : 0);
+        if (NBUF == 1) __syncthreads();                      // single buffer: everybody is done with it before it is refilled
+        if (k1 < ntiles) stage_tile(k1, NBUF == 2 ? (n + 1) & 1 : 0);
+        __syncthreads();
+        k = k1;
+        k1 = s_next[n & 1];
     }
 }
 
-template <class R, int DIM, int TA, int TB, int NT, int MINB, int JC, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false>
-pst_status launch_zrun_k(pst_ctx* ctx, const ZTile& T, size_t smem) {
+template <class R, int DIM, int TA, int TB, int NT, int NBUF, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false>
+pst_status launch_zrun_k(pst_ctx* ctx, const ZTile& T, size_t smem, unsigned grid) {
     const bool rec = rec_wanted(ctx);
     if (rec) PST_TRY(rec_refresh<R>(ctx));
-    auto kern = rec ? k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC> : k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, false, MINB, JC>;
-    if (UNI && rec && CONT && MOM && !COUPLED && DIM == 3 && MINB == 2) {     // timing ablations of the headline kernel (wrong results)
+    auto kern = rec ? k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 0, NBUF> : k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, false, 0, NBUF>;
+    if (UNI && rec && CONT && MOM && !COUPLED && DIM == 3 && sizeof(R) == 8) {     // timing ablations of the headline kernel (wrong results)
         const int dbg = pst_option(ctx, "tile_dbg", 0);
-        if (dbg == 1) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 1>;
-        if (dbg == 2) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 2>;
-        if (dbg == 3) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 3>;
-        if (dbg == 4) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, MINB, JC, 4>;
+        if (dbg == 1) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 1, NBUF>;
+        if (dbg == 3) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 3, NBUF>;
     }
-    PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    const unsigned grid = (unsigned)T.tiles[0] * T.tiles[1] * T.tiles[2];
+    PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WcsphConst<R> C = make_const<R>(ctx);
     if (UNI) fill_uniform<R, DIM>(ctx, C);
     PST_LAUNCH(ctx, kern, grid, NT, smem, make_grid_dev<R>(ctx->grid), C, make_args<R>(ctx), T);
     return PST_OK;
 }
 
-template <class R, int DIM, int TA, int TB, int NT, int MINB, int JC>
+template <class R, int DIM, int NT, int NBUF>
 pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
-    constexpr int kZJcap = JC, kZRow = JC + kZPad;
+    // 2 x 2 columns, 256 threads, two CTAs per SM.  Measured and dropped (profiles/r2_exp_log.txt): 4 x 2 columns with 512 threads
+    // and one CTA per SM (+6 %), three CTAs per SM at 80 registers (+12..21 %: spills, and the third CTA's shared memory leaves too
+    // little L1 for the gathers), prefetch.global.L1 of the next trip's records (+25 %)
+    constexpr int TA = 2, TB = 2;
+    constexpr int kZJcap = zjcap<NT>();
     using D = TileDims<DIM, TA, TB>;
     const PstGrid& g = ctx->grid;
     const int S = g.sub;
@@ -368,43 +479,78 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     double ppc = pst_param(ctx, "_ppc", 0.0);      // mean occupancy of the occupied COARSE cells (k_scan_tiles)
     if (!(ppc > 0)) ppc = DIM == 3 ? 14.0 : 6.0;
     ZTile T;
-    T.maxw = pst_option(ctx, "tile_words", 16);
+    T.maxw = pst_option(ctx, "tile_words", 12);
+    // deepest tile (fine cells): twice the depth that holds one thread per particle at the mean occupancy, bounded by the f32
+    // pre-filter (tile-local coordinates reach gf / S + 6 cells: <= 32 cells keeps the f32 error of r^2 below half of the 2^-15
+    // margin, tests/test_prefilter_margin.py), by the boundary table and by the staging rows
     const int user_G = pst_option(ctx, "tile_g", 0) * S + pst_option(ctx, "tile_gf", 0);   // tile_g in COARSE cells, tile_gf in fine cells
-    // tile depth in fine cells: about one thread per particle
-    int GF = user_G > 0 ? user_G : (int)std::floor(0.95 * NT * S / (D::NI * ppc));
-    GF = std::min(std::max(GF, 1), std::max(1, nf));
-    // f32 pre-filter: tile-local coordinates reach (GF / S + 2 + TA) cells (see test_prefilter_margin.py: <= 32 cells keeps the
-    // f32 error of r^2 below half of the 2^-15 margin)
-    GF = std::min(GF, kMaxTileG * S);
-    // the boundary tables and the staged runs must fit
-    while (GF > 1 && (D::NR * (GF + 2 * S + 1) > 3072 || (user_G <= 0 && 1.10 * D::NR * (GF + 2 * S) * ppc / S + 4 * D::NR > kZJcap))) --GF;
-    T.GF = GF;
-    T.tiles[0] = (g.n[0] + TA - 1) / TA;
-    T.tiles[1] = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
-    T.tiles[2] = (nf + GF - 1) / GF;
+    int gfcap = user_G > 0 ? user_G : (int)std::ceil(2.0 * NT * S / (D::NI * ppc));
+    gfcap = std::min(std::max(gfcap, 1), std::max(1, nf));
+    gfcap = std::min(gfcap, kMaxTileG * S);
+    while (gfcap > 1 && D::NR * (gfcap + 2 * S + 1) > 2048) --gfcap;
+    T.gfcap = gfcap;
+    T.wmax = gfcap + 2 * S + 1;
     T.jcap = std::min(kZJcap, std::max(0, pst_option(ctx, "tile_jcap", kZJcap)));
-    const size_t ints = ((size_t)(D::NR * (GF + 2 * S + 1) + D::NR + D::NR + 1 + D::NI + D::NI + 1) * sizeof(int) + 15) & ~(size_t)15;
-    const size_t smem = ints + (size_t)(DIM == 3 ? 3 : 2) * kZRow * sizeof(float) + (size_t)T.maxw * NT * 8;
-    if (smem > 227 * 1024) return pst_fail(ctx, PST_EINVAL, "tile_words too large");
+    // ---- the tile list (device side; rebuilt when the cell table or the cut parameters changed)
+    const int tiles_x = (g.n[0] + TA - 1) / TA, tiles_y = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
+    const int target = user_G > 0 ? 0x3fffffff : NT;       // a forced depth (tests) cuts by depth alone
+    const size_t cap = (size_t)tiles_x * tiles_y * nf;     // a tile holds at least one fine cell: the list cannot overflow
+    if (cap > ctx->ztiles_cap) {
+        PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->ztiles); ctx->ztiles = nullptr;
+        PST_CUDA(ctx, cudaMalloc(&ctx->ztiles, cap * sizeof(int4)));
+        ctx->ztiles_cap = cap;
+        ctx->ztiles_key = 0;
+    }
+    const int nwarps = tiles_x * tiles_y;
+    if ((size_t)nwarps + 2 > ctx->ztile_off_cap) {
+        PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_ztile_count); ctx->d_ztile_count = nullptr;
+        PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_ztile_count, ((size_t)nwarps + 2) * sizeof(int)));   // [0] dynamic tile counter, [1 ..] tiles per column pair -> offsets
+        ctx->ztile_off_cap = (size_t)nwarps + 2;
+        ctx->ztiles_key = 0;
+    }
+    int* const d_off = ctx->d_ztile_count + 1;
+    const uint64_t key = ctx->build_epoch * 1000003ull + (uint64_t)gfcap * 4099 + (uint64_t)target + (uint64_t)T.jcap * 7919 + (uint64_t)NT * 104729;
+    if (key != ctx->ztiles_key) {
+        PST_CUDA(ctx, cudaMemsetAsync(d_off + nwarps, 0, sizeof(int), ctx->stream));
+        for (int write = 0; write < 2; ++write) {
+            PST_LAUNCH(ctx, (k_ztile_list<DIM, TA, TB>), blocks_for((size_t)nwarps * 32, 128), 128, 0, g.n[0], DIM == 3 ? g.n[1] : 1, nf, g.cx_lo, g.cx_hi,
+                       tiles_x, tiles_y, target, gfcap, S, user_G > 0 ? 0x3fffffff : T.jcap, ctx->cell_start, (int4*)ctx->ztiles, d_off, write);
+            if (!write) PST_TRY(pst_scan_exclusive(ctx, d_off, nwarps + 1));     // off[nwarps] = number of tiles
+        }
+        ctx->ztiles_key = key;
+    }
+    T.tiles = (const int4*)ctx->ztiles;
+    T.ntiles = d_off + nwarps;
+    T.next = ctx->d_ztile_count;
+    constexpr int kZRow = kZJcap + kZPad;
+    const size_t tab_ints = (size_t)((D::NR + D::NR + 1 + D::NI + D::NI + 1 + 4 + NT / 32 + D::NR * T.wmax + 3) & ~3);
+    constexpr int nbuf = NBUF;
+    const size_t smem = nbuf * tab_ints * sizeof(int) + (size_t)nbuf * (DIM == 3 ? 3 : 2) * kZRow * sizeof(float) + (size_t)T.maxw * NT * 6;
+    if (smem > 113 * 1024) return pst_fail(ctx, PST_EINVAL, "tile_words too large (%zu bytes of shared memory per CTA)", smem);
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)((512 / NT) * nsm);        // persistent: 512 threads per SM
+    k_set_int<<<1, 1, 0, ctx->stream>>>(ctx->d_ztile_count, (int)(2 * grid));
     if (ctx->coupled) {
-        if (DIM == 3) return launch_zrun_k<R, 3, TA, TB, NT, MINB, JC, true, true, true>(ctx, T, smem);
+        if (DIM == 3) return launch_zrun_k<R, 3, TA, TB, NT, NBUF, true, true, true>(ctx, T, smem, grid);
         return pst_fail(ctx, PST_EINVAL, "coupled contexts need dim = 3");
     }
     // every particle this rank can see has the same mass AND smoothing length (owned ones: checked on the device; ghosts and
     // migrants of other ranks: the caller vouches for them with "uniform_mass_global"): both become kernel constants
     PST_TRY(pst_uniform_refresh(ctx));
     const bool uni = ctx->m_uniform && ctx->h_uniform && (!ctx->comm || pst_option(ctx, "uniform_mass_global", 0) != 0) && pst_option(ctx, "uniform_mass", 1) != 0;
-    if (cont && mom && uni) return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, true, true, false, true>(ctx, T, smem);
-    if (cont && mom) return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, true, true>(ctx, T, smem);
-    if (cont) return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, true, false>(ctx, T, smem);
-    return launch_zrun_k<R, DIM, TA, TB, NT, MINB, JC, false, true>(ctx, T, smem);
+    if (cont && mom && uni) return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, true, true, false, true>(ctx, T, smem, grid);
+    if (cont && mom) return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, true, true>(ctx, T, smem, grid);
+    if (cont) return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, true, false>(ctx, T, smem, grid);
+    return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, false, true>(ctx, T, smem, grid);
 }
 
 template <class R, int DIM>
 pst_status launch_zrun(pst_ctx* ctx, bool cont, bool mom) {
-    // 2 x 2 columns, 256 threads, two CTAs per SM.  Measured and dropped (profiles/r2_exp_log.txt): 4 x 2 columns with 512 threads
-    // and one CTA per SM (+6 %), three CTAs per SM at 80 registers (+12..21 %: spills, and the third CTA's shared memory leaves too
-    // little L1 for the gathers), prefetch.global.L1 of the next trip's records (+25 %)
-    if (pst_option(ctx, "tile_jc", 0) == 1) return launch_zrun_shape<R, DIM, 2, 2, 256, 2, 1664>(ctx, cont, mom);
-    return launch_zrun_shape<R, DIM, 2, 2, 256, 2, 2304>(ctx, cont, mom);
+    // two CTAs of 256 threads per SM, two staging buffers.  Measured and dropped (profiles/r2_exp_log.txt): one staging buffer
+    // (+2 %), four CTAs of 128 threads with one or two buffers (+8 %)
+    return launch_zrun_shape<R, DIM, 256, 2>(ctx, cont, mom);
 }

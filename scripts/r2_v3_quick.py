@@ -81,7 +81,7 @@ def timing(shape=(200, 200, 250)):
     b = synth.wcsph_block_3d(*shape)
     say(f"timing block {shape}: {b.n} particles")
     base = None
-    for variant, zsub, opts in [(3, 4, {}), (3, 4, {"tile_gf": 16}), (3, 4, {"tile_gf": 15}), (3, 4, {"tile_gf": 16, "tile_jc": 1}), (3, 4, {"tile_gf": 16, "tile_jc": 1, "tile_words": 12}), (3, 4, {"tile_gf": 32, "tile_jc": 0})]:
+    for variant, zsub, opts in [(3, 4, {}), (3, 4, {"tile_cta": 1}), (3, 4, {"tile_cta": 1, "tile_words": 16}), (3, 4, {"tile_cta": 2}), (3, 4, {"tile_cta": 3, "tile_words": 16})]:
         ctx = pb.context_for_block(b)
         try:
             ctx.set_option("zsub", zsub)

@@ -19,7 +19,7 @@ from oracle import oracle as orc                # noqa: E402
 from util import rel_err                        # noqa: E402
 
 
-def _slab_context(whole, rank, world, lr, extra_cap=0, physics="wcsph", max_contacts=0):
+def _slab_context(whole, rank, world, lr, extra_cap=0, physics="wcsph", max_contacts=0, zsub=None):
     cell = whole.cell_size
     n_layers = int(np.ceil((whole.hi[0] - whole.lo[0]) / cell))
     first, k = decomp.split_layers(n_layers, world)[rank]
@@ -29,6 +29,8 @@ def _slab_context(whole, rank, world, lr, extra_cap=0, physics="wcsph", max_cont
     ctx = pb.Context(dim=3, lo=(lo, whole.lo[1], whole.lo[2]), hi=(hi, whole.hi[1], whole.hi[2]), cell_size=cell, capacity=n + extra_cap + 16,
                      physics=physics, max_contacts=max_contacts, device=lr,
                      ghost_capacity=decomp.ghost_capacity(24, 24, cell, whole.meta["dx"]))
+    if zsub is not None:
+        ctx.set_option("zsub", zsub)             # before the communicator: the halo windows are sized by the cell layer
     uid = [pb.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(uid[0], rank, world)
@@ -44,10 +46,12 @@ def halo_parity(out, rank, world, lr):
     whole = synth.wcsph_block_3d(60, 24, 20)
     res = {}
     ref = orc.wcsph(3, whole.params, whole.arrays, grid=orc.make_grid(3, whole.lo, whole.hi, whole.cell_size))
-    for variant in (2, "2g", 1, 0):                # "2g": the tiled kernel without the m[j] gather (every rank uploaded the same mass)
-        ctx, own = _slab_context(whole, rank, world, lr)
-        ctx.set_option("force_kernel", 2 if variant == "2g" else variant)
-        if variant == "2g":
+    # "3g" / "2g": the tiled kernels with m (and h) as constants (every rank uploaded the same values); 1 and 2 cut whole cells
+    for variant in (3, "3g", 2, "2g", 1, 0):
+        fk = int(str(variant)[0])
+        ctx, own = _slab_context(whole, rank, world, lr, zsub=1 if fk in (1, 2) else None)
+        ctx.set_option("force_kernel", fk)
+        if str(variant).endswith("g"):
             ctx.set_option("uniform_mass_global", 1)
         for rep in range(2):                     # second pass: identity re-sort + fresh halo
             ctx.build_neighbours()

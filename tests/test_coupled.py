@@ -126,13 +126,15 @@ def _ctx(block, real, **kw):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("real", [np.float64, np.float32])
-@pytest.mark.parametrize("variant", [2, 0])
+@pytest.mark.parametrize("variant", [3, 2, 0])
 def test_coupled_gpu_one_evaluation(real, variant):
     b = synth.coupled_block_3d(14, 12, 15).shuffled().astype(real)
     nb, ct, margin = _sets(b)
     assert margin > 1e-12 or real == np.float32
     hist = None
     with _ctx(b, real) as ctx:
+        if variant == 2:
+            ctx.set_option("zsub", 1)             # the list kernel cuts its tiles in whole cells
         ctx.set_option("force_kernel", variant)
         for ev in range(3):                       # history carries over; the second and third pass re-sort first
             ref, hist, ov = orc.coupled(b.params, b.max_contacts, b.arrays, hist=hist)

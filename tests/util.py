@@ -18,5 +18,10 @@ def rel_err(got: np.ndarray, ref: np.ndarray) -> float:
 def assert_close(got, ref, what, tol=None):
     tol = TOL[np.dtype(ref.dtype)] if tol is None else tol
     e = rel_err(got, ref)
-    assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
+    if e > tol:    # say how loose the normalisation is for this field: the RMS floor next to the largest reference value
+        r = ref.astype(np.float64)
+        rms, big = float(np.sqrt(np.mean(r * r))) if r.size else 0.0, float(np.max(np.abs(r))) if r.size else 0.0
+        k = int(np.argmax(np.abs(got.astype(np.float64) - r) / np.maximum(np.abs(r), rms if rms > 0 else 1.0))) if r.size else 0
+        raise AssertionError(f"{what}: relative error {e:.3e} > {tol:.1e}  (error / max(|ref|, RMS); RMS(ref) = {rms:.3e}, max|ref| = {big:.3e}; "
+                             f"worst element {k}: got {got.flat[k]!r}, ref {ref.flat[k]!r})")
     return e
