@@ -53,7 +53,7 @@ WcsphConst<R> make_const(pst_ctx* ctx) {
     C.beta = (R)pst_param(ctx, "beta");
     C.g[0] = (R)pst_param(ctx, "gx"); C.g[1] = (R)pst_param(ctx, "gy"); C.g[2] = (R)pst_param(ctx, "gz");
     C.gamma_is_7 = gamma == 7.0;
-    C.u_h = C.u_half_inv_h = C.u_gfc = C.u_eta2 = C.u_rc2 = (R)0;
+    C.u_h = C.u_half_inv_h = C.u_gfc = C.u_eta2 = C.u_rc2 = C.u_mgfc = C.u_visc = (R)0;
     return C;
 }
 
@@ -63,6 +63,7 @@ void fill_uniform(pst_ctx* ctx, WcsphConst<R>& C) {
     IState<R, DIM> I;
     load_i<R, DIM>(I, C, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)0, (R)ctx->h_value);
     C.u_h = I.h; C.u_half_inv_h = I.half_inv_h; C.u_gfc = I.gfc; C.u_eta2 = I.eta2; C.u_rc2 = I.rc2;
+    C.u_mgfc = (R)ctx->m_value * I.gfc; C.u_visc = (R)-2 * C.alpha_c0 * I.h;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -874,12 +875,17 @@ template <class R, int DIM, bool MORTON>
 pst_status launch_forces(pst_ctx* ctx, bool cont, bool mom) {
     int variant = pst_option(ctx, "force_kernel", 3);   // 3 = tiled z-runs + bit masks (default), 2 = thread-per-particle lists, 1 = warp-per-cell, 0 = gather
     if (ctx->coupled && variant == 1) variant = 2;      // the warp-per-cell kernel has no coupled form
+#ifdef PST_DEV_HEADLINE     // kernel-development build (make dev): only the headline instantiation, compiles in seconds
+    if constexpr (sizeof(R) == 8 && DIM == 3 && !MORTON) { if (variant == 3) return launch_zrun<R, DIM>(ctx, cont, mom); }
+    return pst_fail(ctx, PST_EINVAL, "development build: only force_kernel 3, f64, 3D, linear keys");
+#else
     if (variant == 3 && !MORTON) return launch_zrun<R, DIM>(ctx, cont, mom);
     if ((variant == 1 || variant == 2) && !MORTON && ctx->grid.sub != 1)
         return pst_fail(ctx, PST_EINVAL, "force_kernel %d needs zsub = 1 (its tiles are cut in whole cells)", variant);
     if (variant == 1 && !MORTON) return launch_tiled<R, DIM, 1, 2>(ctx, cont, mom);
     if (variant == 2 && !MORTON) return pst_option(ctx, "tile_ta", 2) == 3 ? launch_tiled<R, DIM, 2, 3>(ctx, cont, mom) : launch_tiled<R, DIM, 2, 2>(ctx, cont, mom);
     return launch_gather<R, DIM, MORTON>(ctx, cont, mom);
+#endif
 }
 
 // semi-implicit Euler stage: fluid (tag 0): v += a dt, x += v dt;

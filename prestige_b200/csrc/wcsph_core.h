@@ -42,7 +42,7 @@ struct WcsphConst {
     int gamma_is_7;
     // UNI kernels (every particle has the same smoothing length and mass): the h-derived constants of IState, computed
     // once on the host by the same load_i, so they cost constant-bank operands instead of ten registers per thread
-    R u_h, u_half_inv_h, u_gfc, u_eta2, u_rc2;
+    R u_h, u_half_inv_h, u_gfc, u_eta2, u_rc2, u_mgfc, u_visc;     // u_mgfc = m gfc, u_visc = -2 alpha c0 h
 };
 
 template <class R, int DIM>
@@ -106,28 +106,65 @@ PST_HD float fast_rcp(float x) {
     return 1.0f / x;
 #endif
 }
+// The pair body's own forms.  sqrt(x) = r0 (1 + e/2 + 3 e^2/8) with r0 = x y, e = 1 - r0 y: the same cubically convergent
+// correction as fast_rsqrt applied to r0 directly -- 5 FP64 instructions instead of 6 for x * fast_rsqrt(x), error ~2 ulp.
+// 1/x by ONE Newton step (2 instructions instead of 3): quadratic from the ~2^-22 seed, relative error <= 2^-44 = 6e-14;
+// it only enters the artificial-viscosity term Pi, a small part of the pair force, so the rates stay ~1e-14 from the oracle.
+PST_HD double pair_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double r0 = x * y;
+    const double e = fma(-r0, y, 1.0);                      // 1 - x y^2
+    return fma(r0, e * fma(0.375, e, 0.5), r0);
+#else
+    return sqrt(x);
+#endif
+}
+PST_HD float pair_sqrt(float x) { return x * fast_rsqrt(x); }
+PST_HD double pair_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return fma(y, fma(-x, y, 1.0), y);                      // y (1 + e),  e = 1 - x y
+#else
+    return 1.0 / x;
+#endif
+}
+PST_HD float pair_rcp(float x) { return fast_rcp(x); }
 
 // the pair body (continuity then momentum, the order fuse() keeps: fuse.rs:18,30).
 // caller has already established 0 < r2 < rc2 with the exact test.  Branch-free: one rsqrt, one rcp.
-template <class R, int DIM, bool CONT, bool MOM, bool UNI = false>
+//   BETA0: the quadratic viscosity coefficient is zero (every config of BASELINE.json): Pi = -2 alpha c0 h vx / ((r2 + eta2)(rho_i + rho_j))
+//          costs 2 FP64 multiplies instead of 6 instructions.
+//   FOLD (UNI kernels): the common mass is folded into the kernel-gradient constant (C.u_mgfc = m gfc); `in` masks the pair instead
+//          of a zero mass.
+template <class R, int DIM, bool CONT, bool MOM, bool UNI = false, bool BETA0 = false, bool FOLD = false>
 PST_HD void pair_body(const WcsphConst<R>& C, const IState<R, DIM>& I, R dx, R dy, R dz, R r2, R uj, R vj, R wj,
-                      R rhoj, R mj, R por2j, Acc<R>& a) {
+                      R rhoj, R mj, R por2j, Acc<R>& a, bool in = true) {
     const R half_inv_h = UNI ? C.u_half_inv_h : I.half_inv_h, gfc = UNI ? C.u_gfc : I.gfc, eta2 = UNI ? C.u_eta2 : I.eta2, h = UNI ? C.u_h : I.h;
-    const R r = r2 * fast_rsqrt(r2);
+    const R r = pair_sqrt(r2);
     const R t = (R)1 - r * half_inv_h;
-    const R gf = gfc * (t * t * t);
     const R du = I.u - uj, dv = I.v - vj, dw = DIM == 3 ? I.w - wj : (R)0;
     R vx = du * dx + dv * dy;
     if (DIM == 3) vx += dw * dz;
-    const R mgf = mj * gf;
+    R mgf;
+    if (FOLD) { mgf = C.u_mgfc * (t * t * t); mgf = in ? mgf : (R)0; }
+    else mgf = mj * (gfc * (t * t * t));
     if (CONT) a.arho += mgf * vx;
     if (MOM) {
         // Pi = (beta mu - alpha c0) mu / rho_bar,  mu = h vx / (r2 + eta2),  rho_bar = (rho_i + rho_j)/2
         const R rhos = I.rho + rhoj;
-        const R inv = fast_rcp((r2 + eta2) * rhos);
-        const R wv = h * vx * inv;                          // mu / (2 rho_bar)
-        const R mu = wv * rhos;
-        const R Pi = vx < (R)0 ? (C.beta * mu - C.alpha_c0) * (wv + wv) : (R)0;
+        const R inv = pair_rcp((r2 + eta2) * rhos);
+        R Pi;
+        if (BETA0) {
+            const R k = UNI ? C.u_visc : (R)-2 * C.alpha_c0 * h;     // -2 alpha c0 h
+            Pi = vx < (R)0 ? (k * vx) * inv : (R)0;
+        } else {
+            const R wv = h * vx * inv;                          // mu / (2 rho_bar)
+            const R mu = wv * rhos;
+            Pi = vx < (R)0 ? (C.beta * mu - C.alpha_c0) * (wv + wv) : (R)0;
+        }
         const R c = -mgf * (I.por2 + por2j + Pi);
         a.au += c * dx;
         a.av += c * dy;

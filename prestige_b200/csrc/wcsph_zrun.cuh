@@ -107,7 +107,17 @@ __global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, in
     if (!write && lane == 0) off[wid] = nt;
 }
 
-template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false, bool REC = false, int DBG = 0, int NBUF = 2>
+// predicated shared-memory loads (no branch, no wavefront for lanes whose predicate is off): `old` is returned when p is false
+__device__ __forceinline__ unsigned lds_u32_if(unsigned saddr, bool p, unsigned old) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}" : "+r"(old) : "r"(saddr), "r"((unsigned)p) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned lds_u16_if(unsigned saddr, bool p, unsigned old) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 h;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 {h, _}, %0;\n\t@q ld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "+r"(old) : "r"(saddr), "r"((unsigned)p) : "memory");
+    return old;
+}
+
+template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false, bool REC = false, int DBG = 0, int NBUF = 2, bool BETA0 = false>
 __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, WcsphConst<R> C, ForceArgs<R> A, ZTile T) {
     using D = TileDims<DIM, TA, TB>;
     using P2 = typename RecPair<R>::type;
@@ -360,6 +370,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                     if (full) break;
                     ++k; wc = 0;
                 }
+#ifdef PST_P2_OLD
                 // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
                 {
                     // hit iterator over the mask words (none of them empty): m = bits left in the current word, base31 = global index
@@ -419,6 +430,91 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                         pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx1, dy1, dz1, r21, uj1, vj1, wj1, rj1, m1, pj1, a2);
                     }
                 }
+#else
+                // ---- phase 2: one hit per body, software-pipelined -- the record of the NEXT hit is in flight while the body of
+                // the current one runs (two register sets, loop unrolled by two), so the L1 latency of the gathers hides behind
+                // ~40 FP64 instructions instead of stalling the warp at the head of every trip.  The loop is warp-uniform (runs
+                // until no lane has a hit left); a lane without a hit evaluates a masked dummy pair against a warp-common record.
+                // Exact FMA-free test on the f64 record: the neighbour set is decided here.
+                if (DBG == 3) a.au += (R)nw;      // timing ablation: phase 1 only
+                else {
+                    // hit iterator over the mask words (none empty) with one word of lookahead: m = bits left in the current
+                    // word, base31 = global index of its first candidate + 31; (mN, bN) = the next word, raw; w = the one after
+                    // All of it branch-free (predicated shared-memory loads), so the pipelined loop below is ONE basic block and ptxas
+                    // can hoist a pop and its gathers above the body that precedes them.
+                    const unsigned a_mask = (unsigned)__cvta_generic_to_shared(my_mask), a_base = (unsigned)__cvta_generic_to_shared(my_base);
+                    const unsigned a_gbeg = (unsigned)__cvta_generic_to_shared(s_gbeg);
+                    unsigned m = 0, mN = 0, b16 = 0;
+                    int base31 = 0, baseN = 0, w = 2;
+                    auto word_base = [&](unsigned b) { return (int)(b & 2047u) + s_gbeg[b >> 11] + 31; };
+                    if (nw > 0) { m = my_mask[0]; base31 = word_base(my_base[0]); }
+                    if (nw > 1) { mN = my_mask[NT]; baseN = word_base(my_base[NT]); }
+                    const int jdummy = s_ibeg[0];
+                    auto pop = [&](bool& valid) -> int {
+                        valid = m != 0;
+                        const int c = __clz(m);
+                        int j = base31 - 31 + c;
+                        m &= 0x7fffffffu >> min(c, 31);
+                        const bool adv = valid && m == 0;      // word exhausted: step to the preloaded one, preload the one after
+                        const bool ld = adv && w < nw;
+                        m = adv ? mN : m;
+                        base31 = adv ? baseN : base31;
+                        mN = adv ? 0u : mN;
+                        mN = lds_u32_if(a_mask + (unsigned)w * (NT * 4), ld, mN);
+                        b16 = lds_u16_if(a_base + (unsigned)w * (NT * 2), ld, b16);
+                        const unsigned gq = lds_u32_if(a_gbeg + ((b16 >> 11) << 2), ld, 0u);
+                        baseN = ld ? (int)(b16 & 2047u) + (int)gq + 31 : baseN;
+                        w += adv ? 1 : 0;
+                        j = valid ? j : jdummy;
+                        asm("" : "+r"(j));        // keep j a plain 32-bit value: the record index below is 32-bit arithmetic + one IMAD.WIDE
+                        return j;
+                    };
+                    struct JRec { R x, y, z, u, v, w, rho, por2, m; };
+                    auto load_j = [&](int j) -> JRec {
+                        JRec r;
+                        r.m = A.m_uni;
+                        if (DBG == 1) {     // timing ablation (wrong results): no gathers, the j state is made up from the index
+                            r.x = I.x + (R)(j & 15) * (R)1e-3; r.y = I.y + (R)(j & 7) * (R)1e-3; r.z = I.z; r.u = I.u; r.v = I.v; r.w = (R)j; r.rho = I.rho; r.por2 = I.por2;
+                        } else if (REC) {
+                            const P2* q = reinterpret_cast<const P2*>(A.rec) + rec_index(j);
+                            const P2 a0 = q[0], b0 = q[8], c0 = q[16], d0 = q[24];
+                            r.x = a0.x; r.y = a0.y; r.z = b0.x; r.u = b0.y; r.v = c0.x; r.w = c0.y; r.rho = d0.x; r.por2 = d0.y;
+                            if (!UNI) r.m = q[32].x;
+                        } else {
+                            r.x = A.x[j]; r.y = A.y[j]; r.z = DIM == 3 ? A.z[j] : (R)0; r.u = A.u[j]; r.v = A.v[j]; r.w = DIM == 3 ? A.w[j] : (R)0;
+                            r.rho = A.rho[j]; r.por2 = A.por2[j];
+                            if (!UNI) r.m = A.m[j];
+                        }
+                        return r;
+                    };
+                    const R rc2 = UNI ? C.u_rc2 : I.rc2;
+                    auto body = [&](const JRec& J, bool valid) {
+                        const R dx = I.x - J.x, dy = I.y - J.y, dz = DIM == 3 ? I.z - J.z : (R)0;
+                        R r2 = dist2<DIM, R>(dx, dy, dz);
+                        const bool in = valid && r2 < rc2 && r2 > (R)0;              // the exact test (the set is defined here)
+                        r2 = in ? r2 : (R)1;
+                        R mj = in ? J.m : (R)0;
+                        if (COUPLED) mj = (fluid_i || mj > (R)0) ? fabs(mj) : (R)0;     // signed SPH mass: the pair counts iff i or j is fluid
+                        pair_body<R, DIM, CONT, MOM, UNI, BETA0, UNI && !COUPLED>(C, I, dx, dy, dz, r2, J.u, J.v, J.w, J.rho, mj, J.por2, a, in);
+                    };
+                    // pops run one hit ahead of the gathers, gathers one body ahead of their use
+                    bool vA, vB;
+                    const int jA0 = pop(vA);
+                    JRec rA = load_j(jA0);
+                    int jB = pop(vB);
+                    while (__any_sync(0xffffffffu, vA)) {
+                        const JRec rB = load_j(jB);
+                        const bool vb = vB;
+                        bool vA2;
+                        const int jA2 = pop(vA2);
+                        body(rA, vA);
+                        rA = load_j(jA2);
+                        vA = vA2;
+                        jB = pop(vB);
+                        body(rB, vb);
+                    }
+                }
+#endif
                 if (k == NRUN) break;      // warp-uniform
             }
             if (active) {
@@ -453,10 +549,12 @@ pst_status launch_zrun_k(pst_ctx* ctx, const ZTile& T, size_t smem, unsigned gri
     const bool rec = rec_wanted(ctx);
     if (rec) PST_TRY(rec_refresh<R>(ctx));
     auto kern = rec ? k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 0, NBUF> : k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, false, 0, NBUF>;
+    if (MOM && pst_param(ctx, "beta") == 0.0)      // no quadratic viscosity term (every BASELINE config): the cheaper form of Pi
+        kern = rec ? k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 0, NBUF, MOM> : k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, false, 0, NBUF, MOM>;
     if (UNI && rec && CONT && MOM && !COUPLED && DIM == 3 && sizeof(R) == 8) {     // timing ablations of the headline kernel (wrong results)
         const int dbg = pst_option(ctx, "tile_dbg", 0);
-        if (dbg == 1) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 1, NBUF>;
-        if (dbg == 3) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 3, NBUF>;
+        if (dbg == 1) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 1, NBUF, MOM>;
+        if (dbg == 3) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 3, NBUF, MOM>;
     }
     PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WcsphConst<R> C = make_const<R>(ctx);
@@ -534,6 +632,11 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)((512 / NT) * nsm);        // persistent: 512 threads per SM
     k_set_int<<<1, 1, 0, ctx->stream>>>(ctx->d_ztile_count, (int)(2 * grid));
+#ifdef PST_DEV_HEADLINE
+    PST_TRY(pst_uniform_refresh(ctx));
+    if (!(cont && mom && ctx->m_uniform && ctx->h_uniform && !ctx->coupled)) return pst_fail(ctx, PST_EINVAL, "development build: uniform m and h, continuity + momentum only");
+    return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, true, true, false, true>(ctx, T, smem, grid);
+#else
     if (ctx->coupled) {
         if (DIM == 3) return launch_zrun_k<R, 3, TA, TB, NT, NBUF, true, true, true>(ctx, T, smem, grid);
         return pst_fail(ctx, PST_EINVAL, "coupled contexts need dim = 3");
@@ -546,6 +649,7 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     if (cont && mom) return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, true, true>(ctx, T, smem, grid);
     if (cont) return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, true, false>(ctx, T, smem, grid);
     return launch_zrun_k<R, DIM, TA, TB, NT, NBUF, false, true>(ctx, T, smem, grid);
+#endif
 }
 
 template <class R, int DIM>
