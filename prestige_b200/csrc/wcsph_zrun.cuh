@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
             };
 
             int k = 0, wc = 0;          // warp-uniform scan cursor: stencil run, 32-candidate chunk inside it
-            while (true) {
+            while (DBG != 5) {           // (DBG 5, timing ablation: staging and barriers only)
                 // ---- phase 1: pre-filter on staged f32 coordinates -> bit masks (bit 31 = first candidate of the word)
                 int nw = 0;
                 while (k < NRUN) {
@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                     const int ng = (ve - a4 + 3) >> 2;
                     const int Tg = __reduce_max_sync(0xffffffffu, ve > vs ? ng : 0);   // the warp scans its longest range
                     bool full = false;
+                    if (DBG == 4) { a.au += (R)(vs + ve + Tg); ++k; continue; }      // timing ablation: range set-up only
                     while (wc * 8 < Tg) {
                         if (__any_sync(0xffffffffu, nw == MAXW)) { full = true; break; }
                         const int iters = min(8, Tg - wc * 8);
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                 // ~40 FP64 instructions instead of stalling the warp at the head of every trip.  The loop is warp-uniform (runs
                 // until no lane has a hit left); a lane without a hit evaluates a masked dummy pair against a warp-common record.
                 // Exact FMA-free test on the f64 record: the neighbour set is decided here.
-                if (DBG == 3) a.au += (R)nw;      // timing ablation: phase 1 only
+                if (DBG >= 3) a.au += (R)nw;      // timing ablation: phase 1 only
                 else {
                     // hit iterator over the mask words (none empty) with one word of lookahead: m = bits left in the current
                     // word, base31 = global index of its first candidate + 31; (mN, bN) = the next word, raw; w = the one after
@@ -555,6 +556,8 @@ pst_status launch_zrun_k(pst_ctx* ctx, const ZTile& T, size_t smem, unsigned gri
         const int dbg = pst_option(ctx, "tile_dbg", 0);
         if (dbg == 1) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 1, NBUF, MOM>;
         if (dbg == 3) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 3, NBUF, MOM>;
+        if (dbg == 4) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 4, NBUF, MOM>;
+        if (dbg == 5) kern = k_wcsph_zrun<R, DIM, TA, TB, NT, CONT, MOM, COUPLED, UNI, true, 5, NBUF, MOM>;
     }
     PST_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WcsphConst<R> C = make_const<R>(ctx);
