@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/sec of the NNPS + pair-force hot path on B200 (BASELINE.json metric).
 
-One "step" = cell keys -> radix sort -> cell table -> permute state (-> history remap) -> EOS ->
-fused continuity+momentum pair kernel (or the DEM contact kernel) over one block of synthetic
-particles.  Integrator excluded.
+One "step" = cell keys -> counting sort -> cell table -> permute state (-> history remap) (-> halo exchange) -> EOS ->
+fused continuity+momentum pair kernel (or the DEM contact kernel) over one block of synthetic particles.  Integrator
+excluded from the headline; `moving` in the JSON line times the same step WITH the integrator, so the sort
+works on a permutation that is near the identity but not the identity.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wcsph3d_10m|dem3d_1m|wcsph2d_20k|coupled3d_20m] [--real f64|f32]
-    python bench.py --impl reference ...      # the CPU restatement (oracle/) on the host cores, same metric
-    torchrun --nproc-per-node N bench.py --gpus N ...   # weak scaling: one ~10M-particle x-slab per rank
-                                                        # (coupled3d_20m: STRONG scaling, the 20M block cut into N slabs)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wcsph3d_80m|wcsph3d_10m|dem3d_1m|wcsph2d_20k|coupled3d_20m] [--real f64|f32]
+    python bench.py --impl reference ...      # the CPU restatement (oracle/) on ALL host cores, the SAME workload config
+    torchrun --nproc-per-node N bench.py --gpus N ...
+
+Headline workload = BASELINE configs[3], the 3D WCSPH tank of 80 M particles (800 x 400 x 250 lattice): it fits one B200,
+and --gpus N cuts the SAME tank into N x-slabs, so the per-N values form the STRONG-scaling curve north_star asks for.
+The line also carries `extra_configs` (N = 1 only): short runs of configs[2] (10 M, the size the single-GPU roofline target
+is quoted on), configs[1] (DEM 1 M), configs[0] (2D dam break) and a 2 M coupled block, each with its own stage split.
 
 Prints ONE JSON line (rank 0).
 """
@@ -31,17 +36,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle_steps_per_sec"
 UNIT = "particle-steps/s"
+DEFAULT_WORKLOAD = "wcsph3d_80m"
 
 # algorithmic (compulsory) bytes per particle-step, SURVEY.md 8d / BASELINE.md 4
 B_ALG = {("wcsph", 3, "f64"): 350, ("wcsph", 3, "f32"): 202, ("wcsph", 2, "f64"): 286, ("wcsph", 2, "f32"): 166}
 B_FORCE = {("wcsph", 3, "f64"): 117, ("wcsph", 3, "f32"): 61, ("wcsph", 2, "f64"): 93, ("wcsph", 2, "f32"): 49}
-
 
 # algorithmic f64 flop per particle of the fused pair kernel (SURVEY.md 8d "FLOP figure for the co-bound"): ~8 flop per
 # candidate of the 27 (9) cell stencil + ~70 flop per in-range pair, at h = 1.2 dx, cutoff 2h, cell = cutoff:
 # 3D 373 candidates / 58 neighbours, 2D 52 / 18.  Peak: scripts/ubench/fp64_peak.cu, profiles/ubench_fp64_peak.txt.
 FLOP_FORCE = {3: 8 * 373 + 70 * 58, 2: 8 * 52 + 70 * 18}
 FP64_PEAK_TFLOPS = 36.5
+
+TANK = (800, 400, 250)      # configs[3]: lattice planes of the 80 M tank (dx = 0.005)
+DX = 0.005
 
 
 def dem_bytes(real: str, zbar: float):
@@ -66,6 +74,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_threads() -> int:
+    """Host threads the CPU arm may use: every core this process is allowed on (torchrun's OMP_NUM_THREADS=1 must not decide)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
@@ -73,53 +89,63 @@ def measured_peaks():
 HALO_DESC = {"2": "peer-memory halo (pack kernel stores into the neighbour's cudaIpc buffer over NVLink, epoch flag, wait+unpack kernel)",
              "1": "one packed NCCL send/recv message per neighbour", "0": "per-array NCCL send/recv halo with count hand-shake"}.get(
                  os.environ.get("PST_HALO_IMPL", "2"), "peer-memory halo")
-SLAB_CELLS = 83   # multi-GPU: every rank owns 83 cell layers (0.996 m, ~199.2 lattice planes, ~9.96 M particles)
+SLAB_CELLS = 83   # weak-scaling family: every rank owns 83 cell layers (0.996 m, ~199.2 lattice planes, ~9.96 M particles)
+
+
+def _slab_of(gen, nx, ny, nz, rank, world, **kw):
+    """x-slab `rank` of `world` of the lattice block gen(nx, ny, nz): whole cell layers, near-equal split; the slab is generated
+    directly (counter-based generator), never the whole block."""
+    from prestige_b200 import decomp, synth
+    cell = 2.0 * 1.2 * DX * synth.CELL_MARGIN
+    first, k = decomp.split_layers(int(math.ceil(nx * DX / cell)), world)[rank]
+    lo_x, hi_x = first * cell, (first + k) * cell
+    p0 = max(0, int(math.floor(lo_x / DX)) - 1)
+    p1 = min(nx, int(math.ceil(hi_x / DX)) + 1)
+    b = gen(p1 - p0, ny, nz, dx=DX, ix0=p0, nx_total=nx, **kw)
+    keep = decomp.owner_mask(b.arrays["x"], lo_x, hi_x, rank == 0, rank == world - 1)
+    b.arrays = {k_: np.ascontiguousarray(v[keep]) for k_, v in b.arrays.items()}
+    b.meta["ids"] = b.meta["ids"][keep]
+    return b, (lo_x, hi_x)
 
 
 def make_block(workload: str, rank: int = 0, world: int = 1):
+    """-> (block, slab or None, scaling).  world > 1: the x-slab of this rank."""
     from prestige_b200 import synth
-    if workload == "wcsph3d_10m":
+    if workload == "wcsph3d_80m":              # configs[3]; N > 1 cuts the SAME tank into x-slabs: strong scaling
         if world == 1:
-            return synth.wcsph_block_3d(200, 200, 250, name="wcsph3d_10m"), None
-        # weak scaling (configs[3] family): global tank of world*83 cell layers along x, slab per rank
-        dx = 0.005
-        cell = 2.0 * 1.2 * dx * synth.CELL_MARGIN
+            return synth.wcsph_block_3d(*TANK, name="wcsph3d_80m"), None, "strong"
+        b, slab = _slab_of(synth.wcsph_block_3d, *TANK, rank, world, name="wcsph3d_80m_slab")
+        return b, slab, "strong"
+    if workload == "wcsph3d_10m":              # configs[2]; N > 1: WEAK scaling, one ~10 M slab of 83 cell layers per rank
+        if world == 1:
+            return synth.wcsph_block_3d(200, 200, 250, name="wcsph3d_10m"), None, "weak"
+        cell = 2.0 * 1.2 * DX * synth.CELL_MARGIN
         lo_x, hi_x = rank * SLAB_CELLS * cell, (rank + 1) * SLAB_CELLS * cell
-        nx_total = int(math.floor(world * SLAB_CELLS * cell / dx))
-        p0 = max(0, int(math.floor(lo_x / dx)) - 1)
-        p1 = min(nx_total, int(math.ceil(hi_x / dx)) + 1)
-        b = synth.wcsph_block_3d(p1 - p0, 200, 250, dx=dx, ix0=p0, nx_total=nx_total, name="wcsph3d_10m_slab")
+        nx_total = int(math.floor(world * SLAB_CELLS * cell / DX))
+        p0 = max(0, int(math.floor(lo_x / DX)) - 1)
+        p1 = min(nx_total, int(math.ceil(hi_x / DX)) + 1)
+        b = synth.wcsph_block_3d(p1 - p0, 200, 250, dx=DX, ix0=p0, nx_total=nx_total, name="wcsph3d_10m_slab")
         keep = (b.arrays["x"] >= lo_x) & (b.arrays["x"] < hi_x)
         b.arrays = {k: np.ascontiguousarray(v[keep]) for k, v in b.arrays.items()}
         b.meta["ids"] = b.meta["ids"][keep]
-        return b, (lo_x, hi_x)
-    if workload.startswith("coupled3d_"):   # configs[4]: rigid spheres in fluid; N > 1 cuts the SAME block into x-slabs (strong scaling)
-        from prestige_b200 import decomp
+        return b, (lo_x, hi_x), "weak"
+    if workload.startswith("coupled3d_"):      # configs[4]: rigid spheres in fluid; N > 1 cuts the SAME block (strong scaling)
         nx, ny, nz = {"20m": (250, 250, 320), "2m": (125, 125, 128), "300k": (64, 64, 72)}[workload.split("_")[1]]
         if world == 1:
-            return synth.coupled_block_3d(nx, ny, nz), None
-        dx = 0.005
-        cell = 2.0 * 1.2 * dx * synth.CELL_MARGIN
-        first, k = decomp.split_layers(int(math.ceil(nx * dx / cell)), world)[rank]
-        lo_x, hi_x = first * cell, (first + k) * cell
-        p0 = max(0, int(math.floor(lo_x / dx)) - 1)
-        p1 = min(nx, int(math.ceil(hi_x / dx)) + 1)
-        b = synth.coupled_block_3d(p1 - p0, ny, nz, dx=dx, ix0=p0, nx_total=nx)
-        keep = decomp.owner_mask(b.arrays["x"], lo_x, hi_x, rank == 0, rank == world - 1)
-        b.arrays = {k_: np.ascontiguousarray(v[keep]) for k_, v in b.arrays.items()}
-        b.meta["ids"] = b.meta["ids"][keep]
-        return b, (lo_x, hi_x)
-    if workload == "wcsph3d_80m":          # configs[3] on ONE GPU (strong-scaling reference point): 800 x 400 x 250
-        return synth.wcsph_block_3d(800, 400, 250, name="wcsph3d_80m"), None
+            return synth.coupled_block_3d(nx, ny, nz), None, "strong"
+        b, slab = _slab_of(synth.coupled_block_3d, nx, ny, nz, rank, world)
+        return b, slab, "strong"
+    if world > 1:
+        raise SystemExit("multi-GPU is implemented for the slab workloads wcsph3d_80m (strong), wcsph3d_10m (weak) and coupled3d_* (strong)")
     if workload == "dem3d_1m":
-        return synth.dem_column_3d(100), None
+        return synth.dem_column_3d(100), None, "strong"
     if workload == "dem3d_8m":
-        return synth.dem_column_3d(200), None
+        return synth.dem_column_3d(200), None, "strong"
     if workload == "wcsph2d_20k":
-        return synth.wcsph_dambreak_2d(dx=0.01), None
-    if workload.startswith("wcsph3d_"):     # e.g. wcsph3d_1m: cubes for quick runs
+        return synth.wcsph_dambreak_2d(dx=0.01), None, "strong"
+    if workload.startswith("wcsph3d_"):        # e.g. wcsph3d_1m: cubes for quick runs
         n = {"1m": (100, 100, 100), "2m": (100, 100, 200), "500k": (100, 100, 50)}[workload.split("_")[1]]
-        return synth.wcsph_block_3d(*n, name=workload), None
+        return synth.wcsph_block_3d(*n, name=workload), None, "strong"
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -175,44 +201,41 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's timed step on a bounded sample of the same workload
+# CPU arm: the oracle's cell-list step on the SAME workload config, all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_block(workload: str):
-    from prestige_b200 import synth
-    if workload.startswith("wcsph3d"):
-        return synth.wcsph_block_3d(100, 100, 100), "first 100x100x100 lattice planes (1.0 M particles) of the same generator"
-    if workload.startswith("dem3d"):
-        return synth.dem_column_3d(64), "64^3 spheres + floor (0.27 M particles) of the same generator"
-    if workload.startswith("coupled3d"):
-        return synth.coupled_block_3d(100, 100, 96), "100x100x96 lattice + floor (0.99 M particles, 10 % spheres) of the same generator"
-    return synth.wcsph_dambreak_2d(dx=0.01), "the full 2D dam break (23 k particles)"
-
-
-def cpu_step_time(block, reps: int):
+def oracle_step_fn(block):
+    """One CPU step of the same path (key + sort + permute + EOS + pair loop, cell-list mode) on `block`; returns a callable."""
     from oracle import oracle as orc
+    orc.set_num_threads(host_threads())
     g = orc.make_grid(block.dim, block.lo, block.hi, block.cell_size)
-    best = float("inf")
-    hist = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
+    state = {"hist": None}
+
+    def one():
         if block.physics == "wcsph":
             orc.wcsph(block.dim, block.params, block.arrays, grid=g, sorted_step=True)
         elif block.physics == "dem":
-            _, hist, _ = orc.dem(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
+            _, state["hist"], _ = orc.dem(block.params, block.max_contacts, block.arrays, hist=state["hist"], grid=g)
         else:
-            _, hist, _ = orc.coupled(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
-        best = min(best, time.perf_counter() - t0)
-    return best, orc.num_threads()
+            _, state["hist"], _ = orc.coupled(block.params, block.max_contacts, block.arrays, hist=state["hist"], grid=g)
+    return one, orc.num_threads()
 
 
-def cpu_baseline(workload: str, budget_s: float = 20.0):
-    block, desc = cpu_sample_block(workload)
-    t1, cores = cpu_step_time(block, 1)
-    reps = int(max(1, min(5, budget_s / max(t1, 1e-3) - 1)))
-    t, cores = cpu_step_time(block, reps) if reps > 1 else (t1, cores)
-    t = min(t, t1)
+def cpu_baseline(workload: str, block=None, budget_s: float = 25.0):
+    """The CPU restatement timed on rank 0's host cores on the FULL workload config (the whole block, not a slab): one warm-up
+    step when the budget allows, then as many timed steps as fit ~budget_s (at least one), best-of."""
+    if block is None:
+        block, _, _ = make_block(workload)
+    one, cores = oracle_step_fn(block)
+    t0 = time.perf_counter(); one(); t1 = time.perf_counter() - t0
+    times = [t1]
+    spent = t1
+    while spent + min(times) < budget_s and len(times) < 6:
+        t0 = time.perf_counter(); one(); dt = time.perf_counter() - t0
+        times.append(dt); spent += dt
+    t = min(times)
     out = {"value": block.n / t, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": f"{desc}; oracle cell-list step (key+sort+permute+EOS+pair loop), best of {reps + 1}, {t * 1e3:.1f} ms/step"}
+           "sample": f"the full {workload} block ({block.n} particles), same generator and seed; oracle cell-list step "
+                     f"(key+sort+permute+EOS+pair loop), best of {len(times)}, {t * 1e3:.1f} ms/step"}
     if workload == "wcsph2d_20k":
         # SURVEY.md 8d: for configs[0] also the loop the reference's back-end actually emits (simple_cpu.rs:7-8): all pairs,
         # one thread -- "reference loop semantics as written"
@@ -230,38 +253,67 @@ def cpu_baseline(workload: str, budget_s: float = 20.0):
 
 
 def run_reference(args, rank: int):
+    """--impl reference: the reference has no runnable path, so this arm times the CPU restatement (oracle/) of the
+    same path on ALL host cores, on the SAME workload config as the GPU arm (the whole block: the CPU does not decompose).  Steps are
+    full-size; the run is bounded in time instead (steps are cut, never particles), and the line says how many steps ran."""
     if rank != 0:
         return
-    block, desc = cpu_sample_block(args.workload)
-    from oracle import oracle as orc
-    g = orc.make_grid(block.dim, block.lo, block.hi, block.cell_size)
-    hist = None
-
-    def one():
-        nonlocal hist
-        if block.physics == "wcsph":
-            orc.wcsph(block.dim, block.params, block.arrays, grid=g, sorted_step=True)
-        elif block.physics == "dem":
-            _, hist, _ = orc.dem(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
-        else:
-            _, hist, _ = orc.coupled(block.params, block.max_contacts, block.arrays, hist=hist, grid=g)
+    block, _, scaling = make_block(args.workload)
+    one, cores = oracle_step_fn(block)
+    budget = float(os.environ.get("PST_REF_BUDGET_S", "150"))
+    t_start = time.perf_counter()
+    t_w = []
     for _ in range(args.warmup):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one()
-    dt = time.perf_counter() - t0
-    val = block.n * args.steps / dt
-    real = args.real
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong" if args.workload.startswith("coupled3d") else "weak",
-            "vs_baseline": None, "dtype": real, "data": "synthetic",
-            "config": {"workload": args.workload, "sample": desc, "note": "CPU restatement (oracle/), not reference code: the reference has no runnable path (SURVEY.md 0.1)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": desc},
+        t0 = time.perf_counter(); one(); t_w.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > 0.25 * budget:
+            break
+    est = min(t_w) if t_w else None
+    done, t_total = 0, 0.0
+    while done < args.steps:
+        if done >= 1 and est is not None and (time.perf_counter() - t_start) + est > budget:
+            break
+        t0 = time.perf_counter(); one(); dt = time.perf_counter() - t0
+        t_total += dt; done += 1
+        est = dt if est is None else min(est, dt)
+    val = block.n * done / t_total
+    desc = (f"the full {args.workload} block ({block.n} particles), same generator and seed; {done} of the requested {args.steps} steps "
+            f"(time budget {budget:.0f} s), {len(t_w)} warm-up")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": len(t_w), "ms_per_step": t_total / done * 1e3, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": args.real, "data": "synthetic",
+            "config": workload_config(args.workload, block, 1, args.real, args.key),
+            "note": "CPU restatement (oracle/), not reference code: the reference has no runnable path (SURVEY.md 0.1)",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, block, world, real, key, n_total=None):
+    """The config keys both arms print (so the driver's same-config check compares like with like)."""
+    n_total = block.n if n_total is None else n_total
+    return {"workload": workload, "particles": int(n_total), "dim": block.dim, "physics": block.physics, "real": real, "key": key,
+            "geometry": {"wcsph3d_80m": "800 x 400 x 250 jittered lattice, dx = 0.005 (BASELINE configs[3])",
+                         "wcsph3d_10m": "200 x 200 x 250 jittered lattice, dx = 0.005 (BASELINE configs[2])",
+                         "dem3d_1m": "100^3 spheres + floor (BASELINE configs[1])", "wcsph2d_20k": "2D dam break, dx = 0.01 (BASELINE configs[0])",
+                         "coupled3d_20m": "250 x 250 x 320 lattice + floor, 10 % spheres (BASELINE configs[4])"}.get(workload, workload),
+            "timed": "keys+sort+cell table+permute" + ("+history remap" if block.physics != "wcsph" else "") +
+                     ("+contact kernel" if block.physics == "dem" else "+EOS+fused pair kernel" + ("+contact kernel" if block.physics == "wcsph+dem" else "")) +
+                     " (+migration+halo exchange between slabs when decomposed); integrator excluded",
+            "l2": l2_note(block, n_total, real)}
+
+
+def l2_note(block, n_total, real):
+    if block.physics == "dem":
+        b_step = dem_bytes(real, 6.0)[0]
+    elif block.physics == "wcsph+dem":
+        b_step = coupled_bytes(real, 2.0, 0.1)[0]
+    else:
+        b_step = B_ALG[(block.physics, block.dim, real)]
+    mb = n_total * b_step / 1e6
+    if mb > 4 * 126:
+        return f"no flush needed: ~{mb:.0f} MB of state + outputs touched per step >> 126 MB L2"
+    return f"inputs (~{mb:.0f} MB per step) fit the 126 MB L2: launch-bound configuration, reported as measured"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -287,57 +339,103 @@ class Pinned:
         self.ptrs = []
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="wcsph3d_10m")
-    ap.add_argument("--real", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--force-kernel", type=int, default=2)
-    ap.add_argument("--key", default="linear", choices=["linear", "morton"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--opt", action="append", default=[], help="name=int kernel option (pst_set_option)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+def traffic_for(kernel_mangled: str, workload: str, real: str):
+    """dram bytes per launch of the dominant kernel from profiles/traffic.json (written by scripts/ncu_traffic.py from an
+    `ncu --set full` capture).  Keyed by the MANGLED kernel symbol: an entry for another instantiation never matches."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, "no profiles/traffic.json"
+    with open(tp) as f:
+        t = json.load(f)
+    for e in t.get("entries", []):
+        if e.get("kernel_mangled") == kernel_mangled and e.get("workload") == workload and e.get("real") == real:
+            return e.get("dram_bytes_per_launch"), e.get("source")
+    return None, "no ncu capture of this kernel instantiation on this workload (profiles/traffic.json holds others)"
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
 
-    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
-    import torch
-    import torch.distributed as dist
-    import prestige_b200 as pb
-    from prestige_b200 import _lib
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU restatement)")
-    torch.cuda.set_device(local_rank)
+def parity_check(ctx, block, slab, rank, world, dist, torch):
+    """In-line correctness check of the timed configuration (WCSPH slabs / blocks): this rank's rates against the CPU oracle on a
+    band two cells either side of each of its slab faces (single GPU: of the mid plane), matched by global id; plus
+    sum m (a - g) = 0 (pairwise antisymmetry) and particle-count conservation over all ranks."""
+    from oracle import oracle as orc
+    from prestige_b200 import synth
+    if block.physics != "wcsph" or block.dim != 3 or "lattice" not in block.meta:
+        return None
+    orc.set_num_threads(max(1, host_threads() // world))
+    cell = block.cell_size
+    ny, nz = block.meta["lattice"][1], block.meta["lattice"][2]
+    nx_total = block.meta.get("nx_total", block.meta["lattice"][0])
+    dx = block.meta.get("dx", DX)
+    faces = []
+    if slab is None:
+        faces.append(0.5 * (block.lo[0] + block.hi[0]))
+    else:
+        if rank > 0: faces.append(slab[0])
+        if rank < world - 1: faces.append(slab[1])
+    gid = ctx.download("id").astype(np.int64) if world > 1 else None
+    x = ctx.download("x")
+    got = {c: ctx.download(c) for c in ("au", "av", "aw", "arho")}
+    if world == 1:
+        gid = block.meta["ids"].astype(np.int64)       # host arrays are in id order = generator order
+    worst, checked = 0.0, 0
+    for xf in faces:
+        p0 = max(0, int(math.floor((xf - 2.02 * cell) / dx)))
+        p1 = min(nx_total, int(math.ceil((xf + 2.02 * cell) / dx)) + 1)
+        sub = synth.wcsph_block_3d(p1 - p0, ny, nz, dx=dx, ix0=p0, nx_total=nx_total)
+        ref = orc.wcsph(3, sub.params, sub.arrays, grid=orc.make_grid(3, (p0 * dx - 1e-9, 0.0, 0.0), (p1 * dx + 1e-9, sub.hi[1], sub.hi[2]), cell))
+        sid = sub.meta["ids"].astype(np.int64)
+        inner = np.abs(sub.arrays["x"] - xf) < 0.98 * cell           # complete neighbourhoods inside the sub-block
+        order = np.argsort(sid[inner]); sid_in = sid[inner][order]
+        mine = np.abs(x - xf) < 0.98 * cell
+        pos = np.searchsorted(sid_in, gid[mine])
+        ok = (pos < len(sid_in)) & (sid_in[np.minimum(pos, len(sid_in) - 1)] == gid[mine])
+        if not ok.all():
+            return {"ok": False, "error": "a particle of the band is missing from the oracle's sub-block"}
+        for c in got:
+            r = ref[c][inner][order][pos]
+            scale = float(np.sqrt(np.mean(ref[c] ** 2)))
+            worst = max(worst, float(np.max(np.abs(got[c][mine] - r) / np.maximum(np.abs(r), scale))))
+        checked += int(mine.sum())
+    m = ctx.download("m")
+    g = [block.params.get("gx", 0.0), block.params.get("gy", 0.0), block.params.get("gz", 0.0)]
+    mom = np.array([np.sum(m * (got["au"] - g[0])), np.sum(m * (got["av"] - g[1])), np.sum(m * (got["aw"] - g[2])),
+                    np.sum(m * np.abs(got["au"])), float(ctx.n), float(checked), worst], dtype=np.float64)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.tensor(mom, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(t)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        mom = t.cpu().numpy(); worst = float(tmax[6])
+    n_expected = nx_total * ny * nz
+    res = {"ok": bool(worst < 1e-10 and int(mom[4]) == n_expected and abs(mom[0]) + abs(mom[1]) + abs(mom[2]) < 1e-9 * mom[3]),
+           "max_rel_err_vs_oracle": worst, "tolerance": 1e-10, "particles_checked": int(mom[5]),
+           "bands": "two-cell bands around every slab face" if slab is not None else "two-cell band around the mid plane",
+           "sum_m_a_over_sum_m_abs_a": float((abs(mom[0]) + abs(mom[1]) + abs(mom[2])) / max(mom[3], 1e-300)),
+           "particles_total": int(mom[4]), "particles_expected": int(n_expected)}
+    return res
+
+
+def run_gpu(workload, args, rank, world, local_rank, torch, dist, *, steps, warmup, do_e2e, do_parity, do_moving):
+    """One timed GPU run of `workload`; returns the pieces of the JSON line (rank 0) or None (other ranks)."""
+    import prestige_b200 as pb
+    from prestige_b200 import _lib, decomp
     real = np.float64 if args.real == "f64" else np.float32
-    block, slab = make_block(args.workload, rank, world)
+    t_gen = time.perf_counter()
+    block, slab, scaling = make_block(workload, rank, world)
     block = block.astype(real)
+    t_gen = time.perf_counter() - t_gen
     n = block.n
     ghost_cap = 0
     lo, hi = list(block.lo), list(block.hi)
     if world > 1:
-        if slab is None:
-            raise SystemExit("multi-GPU is implemented for the wcsph3d_10m (weak) and coupled3d_* (strong) slab workloads")
         lo[0], hi[0] = slab
         ny_p, nz_p = block.meta["lattice"][1], block.meta["lattice"][2]
         ghost_cap = int(1.1 * ny_p * (nz_p + 3) * 3)    # a cell layer holds at most 3 lattice planes; also the halo window size
     cap = int(n * 1.02) + 1024
     ctx = pb.Context(dim=block.dim, lo=lo, hi=hi, cell_size=block.cell_size, capacity=cap, real=real, physics=block.physics,
                      key=args.key, max_contacts=block.max_contacts, device=local_rank, ghost_capacity=ghost_cap)
-    ctx.set_option("force_kernel", args.force_kernel)
+    if args.force_kernel is not None:
+        ctx.set_option("force_kernel", args.force_kernel)
     for o in args.opt:
         k, v = o.split("=")
         ctx.set_option(k, int(v))
@@ -346,11 +444,12 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
     ctx.load_block(block)
-    if world > 1 and "m" in block.arrays:
-        # the single-rank run skips the m[j] gather because every uploaded mass is equal; across ranks only the caller can know
-        # that: tell the library when min == max over ALL ranks' particles, so every N times the same kernel
-        from prestige_b200 import decomp
-        if decomp.uniform_across_ranks(block.arrays["m"], dist, device="cuda"):
+    if world > 1:
+        ctx.upload("id", block.meta["ids"].astype(np.uint32))      # distributed mode: global labels, device-order transfers
+        if "m" in block.arrays and decomp.uniform_across_ranks(block.arrays["m"], dist, device="cuda") and \
+                decomp.uniform_across_ranks(block.arrays["h"], dist, device="cuda"):
+            # the single-rank run skips the m[j] gather because every uploaded mass is equal; across ranks only the caller can
+            # know that: tell the library when min == max over ALL ranks' particles, so every N times the same kernel
             ctx.set_option("uniform_mass_global", 1)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     coupled = block.physics == "wcsph+dem"
@@ -377,49 +476,80 @@ def main():
         torch.cuda.synchronize()
         ctx.sync()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
     l0 = ctx.stat("launches")
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         step(evs[k])
     barrier()
     wall = time.perf_counter() - t0
     launches = ctx.stat("launches") - l0
     clocks = sampler.stop() if rank == 0 else None
     t_dev = evs[0][0].elapsed_time(evs[-1][4]) * 1e-3         # device time of the whole timed region
-    t_nnps = sum(e[0].elapsed_time(e[1]) for e in evs) * 1e-3 / args.steps
-    t_eos = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / args.steps
-    t_force = sum(e[2].elapsed_time(e[3]) for e in evs) * 1e-3 / args.steps
-    t_dem = sum(e[3].elapsed_time(e[4]) for e in evs) * 1e-3 / args.steps
+    t_nnps = sum(e[0].elapsed_time(e[1]) for e in evs) * 1e-3 / steps
+    t_eos = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / steps
+    t_force = sum(e[2].elapsed_time(e[3]) for e in evs) * 1e-3 / steps
+    t_dem = sum(e[3].elapsed_time(e[4]) for e in evs) * 1e-3 / steps
+    kern_mangled = ctx.kernel_name("contact" if block.physics == "dem" else "pair", demangle=False)
+    kern = ctx.kernel_name("contact" if block.physics == "dem" else "pair")
     zbar, n_solid = 0.0, 0
     if block.physics == "dem":
         zbar = ctx.stat("contacts_total") / n
     elif coupled:
         n_solid = int((block.arrays["tag"] == 2).sum())
         zbar = ctx.stat("contacts_total") / max(n_solid, 1)     # mean stored contacts per SPHERE
-    n_total, t_max = n, t_dev
+    n_total, t_max, t_force_max = n, t_dev, t_force
     if world > 1:
-        tt = torch.tensor([t_dev, wall], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_dev, wall, t_force], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_max = float(tt[0])
+        t_max, t_force_max = float(tt[0]), float(tt[2])
         nn = torch.tensor([n, n_solid, int(round(zbar * n_solid))], device="cuda", dtype=torch.int64)
         dist.all_reduce(nn)
         n_total, n_solid_total = int(nn[0]), int(nn[1])
         zbar_total = float(nn[2]) / max(n_solid_total, 1)
     else:
         n_solid_total, zbar_total = n_solid, zbar
-    value = n_total * args.steps / t_max
+    value = n_total * steps / t_max
+
+    # ---- in-line correctness of exactly this configuration (every N)
+    parity = None
+    if do_parity:
+        step()
+        parity = parity_check(ctx, block, slab, rank, world, dist, torch)
+
+    # ---- the same step WITH the integrator: particles move, the re-sort permutes (near-identity, not identity)
+    moving = None
+    if do_moving:
+        dt_s = 0.1 * (1.2 * DX if block.dim == 3 and block.physics != "dem" else 1e-3) / max(block.params.get("c0", 1.0), 1.0) if block.physics != "dem" else 1e-6
+        m_steps = max(3, min(steps, 10))
+        ctx.step(dt_s, 2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.step(dt_s, m_steps)
+        e1.record(stream)
+        barrier()
+        tm = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            tt = torch.tensor([tm], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tm = float(tt[0])
+        moving = {"ms_per_step": tm / m_steps * 1e3, "value": n_total * m_steps / tm, "unit": UNIT, "steps": m_steps, "dt": dt_s,
+                  "path": "pst_step: re-sort (+ migration + halo) -> EOS -> pair kernel -> integrator; the sort sees moved particles"}
+        ctx.load_block(block)                    # back to the synthetic state for the end-to-end run
+        if world > 1:
+            ctx.upload("id", block.meta["ids"].astype(np.uint32))
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if do_e2e:
         lib = _lib.load()
         pin = Pinned(lib)
         ins = [k for k in block.arrays if ctx.has_array(k) and k not in ("tag", "m", "h", "rad", "inertia")]
@@ -430,19 +560,25 @@ def main():
             hin[k][:] = block.arrays[k]
         hout = {k: pin.array(n, real) for k in outs}
         h2d = sum(v.nbytes for v in hin.values()); d2h = sum(v.nbytes for v in hout.values())
+        step(); barrier()
+        n_now = ctx.refresh_count()
+        assert n_now == n, "the synthetic block does not move: no particle may have migrated"
+        if world > 1:
+            # distributed mode: host arrays are in DEVICE order (ids are global labels), so the host copy of the state is the
+            # one a coupled code would hold after its last download -- fetch it once, then every step ships it back unchanged
+            for k in ins:
+                hin[k][:] = ctx.download(k)
 
         def e2e_step():
             # the public asynchronous path: H2D of this step's state and D2H of the previous step's rates ride the two
             # copy engines (PCIe is full duplex) while the compute stream works; every byte still crosses every step
-            if world > 1:
-                ctx.set_count(n)                 # distributed mode: host arrays are in device order, so restart from the host order
             for k in ins:
                 ctx.upload_async(k, hin[k].ctypes.data)
             step()
             ctx.wait_transfers()                 # previous step's rates have landed: the host may consume them now
             for k in outs:
                 ctx.download_async(k, hout[k].ctypes.data)
-        e2e_steps = max(3, min(args.steps, 10))
+        e2e_steps = max(3, min(steps, 10))
         for _ in range(3):                       # warm-up: staging ring allocated, pinned pages touched
             e2e_step()
         barrier()
@@ -455,59 +591,117 @@ def main():
             tt = torch.tensor([te], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             te = float(tt[0])
-        e2e = {"value": n_total * e2e_steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": n_total * e2e_steps / te, "unit": UNIT, "h2d_bytes_per_step": h2d * world if world == 1 else int(h2d * n_total / max(n, 1)),
+               "d2h_bytes_per_step": d2h * world if world == 1 else int(d2h * n_total / max(n, 1)),
                "steps": e2e_steps, "ms_per_step": te / e2e_steps * 1e3,
-               "path": f"pst_upload_async({len(ins)} state arrays, pinned host) -> pst_build_neighbours -> pst_apply -> pst_download_async({len(outs)} rate arrays, pinned host), pst_sync at the end"}
+               "path": f"pst_upload_async({len(ins)} state arrays, pinned host) -> pst_build_neighbours -> pst_apply -> pst_download_async({len(outs)} rate arrays, pinned host), pst_sync at the end; bytes are the job's total over all ranks"}
         pin.free()
-
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        key = (block.physics, block.dim, args.real)
-        if block.physics == "dem":
-            b_step, b_force = dem_bytes(args.real, zbar)
-        elif coupled:
-            # the SPH pass of a coupled step touches every particle's SPH columns; the contact pass is reported beside it
-            b_step, _ = coupled_bytes(args.real, zbar_total, n_solid_total / n_total)
-            b_force = B_FORCE[("wcsph", 3, args.real)]
-        else:
-            b_step, b_force = B_ALG[key], B_FORCE[key]
-        n_local = n
-        ach = b_force * n_local / t_force / 1e9
-        kern = ({1: "k_wcsph_cellwarp", 2: "k_wcsph_tiled"}.get(args.force_kernel, "k_wcsph_gather") if args.key == "linear" else "k_wcsph_gather") if block.physics != "dem" else "k_dem_forces"
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(f"{kern}:{args.workload}:{args.real}")
-        roofline = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "peak_source": peak_src, "alg_bytes_per_particle": b_force, "particles_per_launch": n_local,
-                    "kernel_ms": t_force * 1e3,
-                    "step": {"alg_bytes_per_particle": b_step, "achieved": b_step * n_total / (t_max / args.steps) / 1e9 / world,
-                             "frac": b_step * n_total / (t_max / args.steps) / 1e9 / world / peak},
-                    "stage_ms": {"nnps(keys+sort+table+permute" + ("+halo)" if world > 1 else ")"): t_nnps * 1e3, "eos": t_eos * 1e3, "pair_kernel": t_force * 1e3}}
-        if coupled:
-            roofline["stage_ms"]["contact_kernel"] = t_dem * 1e3
-        if args.real == "f64" and block.physics != "dem":
-            # the f64 pair kernel is bound on-chip, not by HBM: its FP64 fraction beside the HBM one
-            tf = FLOP_FORCE[block.dim] * n_local / t_force / 1e12
-            roofline["fp64_cobound"] = {"alg_flop_per_particle": FLOP_FORCE[block.dim], "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                                        "frac": tf / FP64_PEAK_TFLOPS, "peak_source": "measured DFMA rate (profiles/ubench_fp64_peak.txt)"}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if coupled else "weak", "vs_baseline": None,
-                "dtype": args.real, "data": "synthetic",
-                "config": {"workload": args.workload, "particles": n_total, "particles_per_gpu": n_local, "dim": block.dim,
-                           "physics": block.physics, "key": args.key, "force_kernel": kern,
-                           "decomposition": (f"{world} x-slabs of the same block, {HALO_DESC}" if coupled else f"{world} x-slabs of {SLAB_CELLS} cell layers, {HALO_DESC}") if world > 1 else "single GPU",
-                           "l2": f"no flush needed: state + outputs = {n_local * (b_step) / 1e6:.0f} MB touched per step >> 126 MB L2",
-                           "timed": "keys+sort+cell table+permute" + ("+history remap" if block.physics != "wcsph" else "") + ("+halo exchange" if world > 1 else "") + ("+contact kernel" if block.physics == "dem" else "+EOS+fused pair kernel" + ("+contact kernel" if coupled else "")) + "; integrator excluded",
-                           "mean_contacts": zbar_total if block.physics != "wcsph" else None,
-                           "spheres": n_solid_total if coupled else None},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps * 1e3,
-                "roofline": roofline}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.workload)
-        print(json.dumps(line), flush=True)
     ctx.close()
+    if rank != 0:
+        return None
+
+    peak, peak_src = measured_peaks()
+    key = (block.physics, block.dim, args.real)
+    if block.physics == "dem":
+        b_step, b_force = dem_bytes(args.real, zbar)
+    elif coupled:
+        # the SPH pass of a coupled step touches every particle's SPH columns; the contact pass is reported beside it
+        b_step, _ = coupled_bytes(args.real, zbar_total, n_solid_total / n_total)
+        b_force = B_FORCE[("wcsph", 3, args.real)]
+    else:
+        b_step, b_force = B_ALG[key], B_FORCE[key]
+    n_local = n
+    t_kernel = t_force if block.physics != "dem" else t_force
+    ach = b_force * n_local / t_kernel / 1e9
+    traffic, traffic_src = traffic_for(kern_mangled, workload, args.real)
+    roofline = {"bound": "hbm", "kernel": kern, "kernel_mangled": kern_mangled, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "alg_bytes_per_particle": b_force, "particles_per_launch": n_local,
+                "kernel_ms": t_kernel * 1e3,
+                "step": {"alg_bytes_per_particle": b_step, "achieved": b_step * n_total / (t_max / steps) / 1e9 / world,
+                         "frac": b_step * n_total / (t_max / steps) / 1e9 / world / peak},
+                "stage_ms": {"nnps(keys+sort+table+permute" + ("+migration+halo)" if world > 1 else ")"): t_nnps * 1e3, "eos": t_eos * 1e3, "pair_kernel": t_force * 1e3}}
+    if coupled:
+        roofline["stage_ms"]["contact_kernel"] = t_dem * 1e3
+    if args.real == "f64" and block.physics != "dem":
+        # the f64 pair kernel is bound on-chip, not by HBM: its FP64 fraction beside the HBM one
+        tf = FLOP_FORCE[block.dim] * n_local / t_force / 1e12
+        roofline["fp64_cobound"] = {"alg_flop_per_particle": FLOP_FORCE[block.dim], "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                    "frac": tf / FP64_PEAK_TFLOPS, "peak_source": "measured DFMA rate (profiles/ubench_fp64_peak.txt)"}
+    cfg = workload_config(workload, block, world, args.real, args.key, n_total)        # identical keys and values in the CPU arm
+    import re
+    km = re.search(r"(k_\w+)", kern)
+    run = {"particles_per_gpu": n_local, "force_kernel": km.group(1) if km else kern,
+           "decomposition": f"{world} x-slabs of the SAME block (whole cell layers, near-equal split), {HALO_DESC}" if world > 1 and scaling == "strong" else
+                            (f"{world} x-slabs of {SLAB_CELLS} cell layers, {HALO_DESC}" if world > 1 else "single GPU"),
+           "per_gpu_mb_per_step": n_local * b_step / 1e6,
+           "mean_contacts": zbar_total if block.physics != "wcsph" else None,
+           "spheres": n_solid_total if coupled else None}
+    return {"value": value, "ms_per_step": t_max / steps * 1e3, "scaling": scaling, "config": cfg, "run": run, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "wall_ms_per_step": wall / steps * 1e3, "roofline": roofline, "parity_check": parity,
+            "moving": moving, "block": block, "host_s": {"generate_block": t_gen}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--real", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--force-kernel", type=int, default=None, help="pair-kernel variant (default: the library's, 3)")
+    ap.add_argument("--key", default="linear", choices=["linear", "morton"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (short runs of the other BASELINE configs, N = 1)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-moving", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=int kernel option (pst_set_option)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    r = run_gpu(args.workload, args, rank, world, local_rank, torch, dist, steps=args.steps, warmup=args.warmup,
+                do_e2e=not args.no_e2e, do_parity=not args.no_parity, do_moving=not args.no_moving)
+    extras = {}
+    if world == 1 and not args.no_extra and args.workload == DEFAULT_WORKLOAD:
+        for wl, k in (("wcsph3d_10m", 20), ("dem3d_1m", 20), ("wcsph2d_20k", 50), ("coupled3d_2m", 10)):
+            try:
+                x = run_gpu(wl, args, rank, world, local_rank, torch, dist, steps=k, warmup=3, do_e2e=False,
+                            do_parity=wl == "wcsph3d_10m", do_moving=True)
+                extras[wl] = {kk: x[kk] for kk in ("value", "ms_per_step", "config", "run", "roofline", "gpu_launches", "parity_check", "moving")}
+                extras[wl]["steps"] = k
+            except Exception as e:          # an extra must never take the headline down
+                extras[wl] = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None,
+                "dtype": args.real, "data": "synthetic", "config": r["config"], "run": r["run"], "clocks": r["clocks"], "e2e": r["e2e"],
+                "gpu_launches": r["gpu_launches"], "wall_ms_per_step": r["wall_ms_per_step"], "roofline": r["roofline"],
+                "parity_check": r["parity_check"], "moving": r["moving"]}
+        if extras:
+            line["extra_configs"] = extras
+        if not args.no_cpu_baseline and world == 1:       # rank 0 at N = 1 only (at N > 1 the other ranks would idle in a barrier)
+            line["cpu_baseline"] = cpu_baseline(args.workload, r["block"])
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()

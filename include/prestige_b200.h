@@ -153,8 +153,12 @@ PST_API pst_status pst_integrate(pst_ctx* ctx, double dt);
 
 /* counters: n_cells max_cell_count launches pairs_tested contacts_total key_bits ... */
 PST_API pst_status pst_get_stat(pst_ctx* ctx, const char* name, double* value);
+/* mangled symbol of the kernel the last pst_apply launched for `stage` ("pair": the fused continuity / momentum kernel,
+ * "contact": the DEM contact kernel), copied into buf (NUL-terminated, truncated to cap).  For measurement scripts: it is
+ * the name a profiler reports, so a profile can be tied to the kernel a run actually used.  PST_ESTATE before the first launch. */
+PST_API pst_status pst_kernel_name(pst_ctx* ctx, const char* stage, char* buf, size_t cap);
 /* select a kernel variant (A/B measurement): name "force_kernel" value 0 = per-particle gather, 1 = warp per cell, 2 = tiled
- * lists (default).  "uniform_mass" 0 = always gather m[j] (default 1: skip the gather when every uploaded mass is equal);
+ * lists, 3 = tiled z-runs + bit masks (default).  "uniform_mass" 0 = always gather m[j] (default 1: skip the gather when every uploaded mass is equal);
  * "uniform_mass_global" 1 = multi-GPU: the caller guarantees that EVERY rank uploaded the same single mass value, so the
  * skip also applies to ghosts and migrants (default 0: with a communicator m[j] is always gathered). */
 PST_API pst_status pst_set_option(pst_ctx* ctx, const char* name, int value);

@@ -33,7 +33,7 @@ SYMBOLS = [
     "pst_version", "pst_create", "pst_destroy", "pst_last_error", "pst_stream", "pst_sync", "pst_set_param",
     "pst_get_param", "pst_set_count", "pst_get_count", "pst_array_create", "pst_array", "pst_upload",
     "pst_download", "pst_upload_async", "pst_download_async", "pst_wait_transfers", "pst_host_alloc", "pst_host_free", "pst_build_neighbours", "pst_apply", "pst_dump_pairs",
-    "pst_step", "pst_integrate", "pst_get_stat", "pst_set_option", "pst_comm_unique_id", "pst_comm_init",
+    "pst_step", "pst_integrate", "pst_get_stat", "pst_kernel_name", "pst_set_option", "pst_comm_unique_id", "pst_comm_init",
     "pst_halo_exchange", "pst_bodies_create", "pst_bodies_setup", "pst_bodies_restore", "pst_bodies_state",
 ]
 
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     lib.pst_integrate.argtypes = [vp, C.c_double]; lib.pst_integrate.restype = st
     lib.pst_get_stat.argtypes = [vp, cp, C.POINTER(C.c_double)]; lib.pst_get_stat.restype = st
     lib.pst_set_option.argtypes = [vp, cp, C.c_int]; lib.pst_set_option.restype = st
+    lib.pst_kernel_name.argtypes = [vp, cp, C.c_char_p, C.c_size_t]; lib.pst_kernel_name.restype = st
     lib.pst_comm_unique_id.argtypes = [vp]; lib.pst_comm_unique_id.restype = st
     lib.pst_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]; lib.pst_comm_init.restype = st
     lib.pst_halo_exchange.argtypes = [vp]; lib.pst_halo_exchange.restype = st

@@ -196,6 +196,19 @@ class Context:
         self._ck(self._lib.pst_get_stat(self._h, name.encode(), C.byref(v)))
         return v.value
 
+    def kernel_name(self, stage: str = "pair", demangle: bool = True) -> str:
+        """Symbol of the kernel the last apply() launched for `stage` ("pair" | "contact"); demangled with c++filt when available."""
+        buf = C.create_string_buffer(1024)
+        self._ck(self._lib.pst_kernel_name(self._h, stage.encode(), buf, len(buf)))
+        name = buf.value.decode()
+        if demangle:
+            import subprocess
+            try:
+                name = subprocess.run(["c++filt", name], capture_output=True, text=True, timeout=10).stdout.strip() or name
+            except Exception:
+                pass
+        return name
+
     # -- multi-particle rigid bodies (coupled contexts) ---------------------------------------
     _BODY_WIDTH = {"mass": 1, "cm": 3, "vel": 3, "omega": 3, "rot": 9, "inertia0": 6, "force": 3, "torque": 3}
 

@@ -289,7 +289,7 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "upload '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
     if (a->name == "id") return pst_fail(ctx, PST_EINVAL, "'id' is maintained by the library");
-    if (!ctx->ordered || ctx->comm || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / distributed mode / history rows: plain path
+    if ((!ctx->ordered && !ctx->comm) || a->rows != 1) return pst_upload(ctx, name, host, n);   // identity order / history rows: plain path
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     note_uniform_dirty(ctx, a);
     int k = 0;
@@ -297,11 +297,17 @@ pst_status pst_upload_async(pst_ctx* ctx, const char* name, const void* host, si
     PST_CUDA(ctx, cudaMemcpyAsync(ctx->ring[k], host, n * a->esize, cudaMemcpyHostToDevice, ctx->h2d_stream));
     PST_CUDA(ctx, cudaEventRecord(ctx->ring_ready[k], ctx->h2d_stream));
     PST_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ring_ready[k], 0));
-    char* saved = ctx->stage;
-    ctx->stage = ctx->ring[k];
-    const pst_status st = pst_reorder_upload(ctx, a, 0, n);
-    ctx->stage = saved;
-    PST_TRY(st);
+    if (ctx->comm) {
+        // distributed mode: host arrays are in DEVICE order, so the staged copy goes straight into the array -- on the compute
+        // stream, after whatever still reads the array there (a copy engine writing into it directly would race with the step)
+        PST_CUDA(ctx, cudaMemcpyAsync(pst_ptr<char>(ctx, a), ctx->ring[k], n * a->esize, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        char* saved = ctx->stage;
+        ctx->stage = ctx->ring[k];
+        const pst_status st = pst_reorder_upload(ctx, a, 0, n);
+        ctx->stage = saved;
+        PST_TRY(st);
+    }
     PST_CUDA(ctx, cudaEventRecord(ctx->ring_free[k], ctx->stream));
     if (a->name == "x" || a->name == "y" || a->name == "z" || a->name == "rad" || a->name == "h") ctx->nbrs_valid = false;
     if (a->name == "rho" || a->name == "m" || a->name == "tag") ctx->eos_valid = false;
@@ -314,15 +320,19 @@ pst_status pst_download_async(pst_ctx* ctx, const char* name, void* host, size_t
     PstArray* a = pst_find(ctx, name);
     if (!a) return pst_fail(ctx, PST_EINVAL, "unknown array '%s'", name);
     if (n != ctx->n) return pst_fail(ctx, PST_EINVAL, "download '%s': n = %zu but the context holds %llu particles", name, n, (unsigned long long)ctx->n);
-    if (!ctx->ordered || ctx->comm || a->rows != 1 || a->name == "id") return pst_download(ctx, name, host, n);
+    if ((!ctx->ordered && !ctx->comm) || a->rows != 1 || (a->name == "id" && !ctx->comm)) return pst_download(ctx, name, host, n);
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     int k = 0;
     PST_TRY(ring_acquire(ctx, ctx->stream, false, &k));
-    char* saved = ctx->stage;
-    ctx->stage = ctx->ring[k];
-    const pst_status st = pst_reorder_download(ctx, a, 0, n);
-    ctx->stage = saved;
-    PST_TRY(st);
+    if (ctx->comm) {       // distributed mode: device order, a snapshot of the array taken on the compute stream
+        PST_CUDA(ctx, cudaMemcpyAsync(ctx->ring[k], pst_ptr<char>(ctx, a), n * a->esize, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        char* saved = ctx->stage;
+        ctx->stage = ctx->ring[k];
+        const pst_status st = pst_reorder_download(ctx, a, 0, n);
+        ctx->stage = saved;
+        PST_TRY(st);
+    }
     PST_CUDA(ctx, cudaEventRecord(ctx->ring_ready[k], ctx->stream));
     PST_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ring_ready[k], 0));
     PST_CUDA(ctx, cudaMemcpyAsync(host, ctx->ring[k], n * a->esize, cudaMemcpyDeviceToHost, ctx->d2h_stream));
@@ -603,6 +613,18 @@ pst_status pst_step(pst_ctx* ctx, double dt, int n_steps) {
         }
         PST_TRY(pst_integrate(ctx, dt));
     }
+    return PST_OK;
+}
+
+pst_status pst_kernel_name(pst_ctx* ctx, const char* stage, char* buf, size_t cap) {
+    if (!ctx || !stage || !buf || cap == 0) return PST_EINVAL;
+    const std::string s = stage;
+    const void* fn = s == "pair" ? ctx->pair_kernel_fn : s == "contact" ? ctx->contact_kernel_fn : nullptr;
+    if (s != "pair" && s != "contact") return pst_fail(ctx, PST_EINVAL, "unknown stage '%s' (pair | contact)", stage);
+    if (!fn) return pst_fail(ctx, PST_ESTATE, "no '%s' kernel has been launched yet", stage);
+    const char* nm = nullptr;
+    PST_CUDA(ctx, cudaFuncGetName(&nm, fn));
+    std::snprintf(buf, cap, "%s", nm ? nm : "");
     return PST_OK;
 }
 

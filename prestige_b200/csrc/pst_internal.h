@@ -101,6 +101,9 @@ struct pst_ctx {
     unsigned long long *d_uni = nullptr, *h_uni = nullptr;   // min / max bit patterns of m and h (device, pinned mirror)
     bool hist_lag = false;           // contact-history rows still sit at their PRE-sort index (vals_out maps new -> old)
     uint64_t launches = 0;
+    const void* last_kernel_fn = nullptr;        // every PST_LAUNCH records its kernel; the stage entry points keep theirs
+    const void* pair_kernel_fn = nullptr;
+    const void* contact_kernel_fn = nullptr;
     cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)
     bool stats_pending = false;
     PstComm* comm = nullptr;
@@ -140,6 +143,7 @@ struct PstRange {
         auto k__ = kern;                                                                          \
         k__<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                             \
         (ctx)->launches++;                                                                        \
+        (ctx)->last_kernel_fn = (const void*)k__;                                                 \
         PST_CUDA(ctx, cudaGetLastError());                                                        \
     } while (0)
 

@@ -1108,7 +1108,9 @@ pst_status pst_wcsph_eos(pst_ctx* ctx) {
 
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum) {
     if (ctx->n == 0) return PST_OK;
-    return PST_DISPATCH(ctx, launch_forces, ctx, continuity, momentum);
+    PST_TRY(PST_DISPATCH(ctx, launch_forces, ctx, continuity, momentum));
+    ctx->pair_kernel_fn = ctx->last_kernel_fn;
+    return PST_OK;
 }
 
 pst_status pst_coupled_integrate(pst_ctx* ctx, double dt) {

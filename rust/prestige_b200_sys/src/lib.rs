@@ -74,6 +74,7 @@ unsafe extern "C" {
     pub fn pst_step(ctx: *mut pst_ctx, dt: c_double, n_steps: c_int) -> pst_status;
     pub fn pst_integrate(ctx: *mut pst_ctx, dt: c_double) -> pst_status;
     pub fn pst_get_stat(ctx: *mut pst_ctx, name: *const c_char, value: *mut c_double) -> pst_status;
+    pub fn pst_kernel_name(ctx: *mut pst_ctx, stage: *const c_char, buf: *mut c_char, cap: usize) -> pst_status;
     pub fn pst_set_option(ctx: *mut pst_ctx, name: *const c_char, value: c_int) -> pst_status;
     pub fn pst_comm_unique_id(id_bytes: *mut c_void) -> pst_status;
     pub fn pst_comm_init(ctx: *mut pst_ctx, id_bytes: *const c_void, rank: c_int, n_ranks: c_int) -> pst_status;
