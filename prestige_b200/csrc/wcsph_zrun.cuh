@@ -107,14 +107,9 @@ __global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, in
     if (!write && lane == 0) off[wid] = nt;
 }
 
-// predicated shared-memory loads (no branch, no wavefront for lanes whose predicate is off): `old` is returned when p is false
-__device__ __forceinline__ unsigned lds_u32_if(unsigned saddr, bool p, unsigned old) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}" : "+r"(old) : "r"(saddr), "r"((unsigned)p) : "memory");
-    return old;
-}
-__device__ __forceinline__ unsigned lds_u16_if(unsigned saddr, bool p, unsigned old) {
-    asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 h;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 {h, _}, %0;\n\t@q ld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "+r"(old) : "r"(saddr), "r"((unsigned)p) : "memory");
-    return old;
+// predicated 8-byte shared-memory load (no branch, no wavefront for lanes whose predicate is off): a, b keep their values when p is false
+__device__ __forceinline__ void lds_u64_if(unsigned saddr, bool p, unsigned& a, unsigned& b) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}" : "+r"(a), "+r"(b) : "r"(saddr), "r"((unsigned)p) : "memory");
 }
 
 template <class R, int DIM, int TA, int TB, int NT, bool CONT, bool MOM, bool COUPLED = false, bool UNI = false, bool REC = false, int DBG = 0, int NBUF = 2, bool BETA0 = false>
@@ -135,9 +130,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
     int* const s_tab0 = reinterpret_cast<int*>(smem_raw);
     float* const s_row0 = reinterpret_cast<float*>(smem_raw + (size_t)NBUF * tab_ints * sizeof(int));
     constexpr int kRows = DIM == 3 ? 3 : 2;
-    unsigned* const s_mask = reinterpret_cast<unsigned*>(s_row0 + NBUF * kRows * kZRow);   // maxw * NT
-    unsigned short* const s_base = reinterpret_cast<unsigned short*>(s_mask + T.maxw * NT);   // maxw * NT: staged run (<< 11) | staged index of a word's first candidate
-    static_assert(kZRow <= 2048 && NR <= 32, "a word's base packs the staged index in 11 bits and the run in 5");
+    uint2* const s_word = reinterpret_cast<uint2*>(s_row0 + NBUF * kRows * kZRow);   // maxw * NT: (mask, global index of the word's first candidate + 31)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nf = g.n[FAST];                       // fine cells along the fast axis
@@ -147,8 +140,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
     const float cellf = (float)g.cell;
     const float inv_cf = (float)S / cellf;          // 1 / fine cell edge
     const int MAXW = T.maxw;
-    unsigned* const my_mask = s_mask + tid;
-    unsigned short* const my_base = s_base + tid;
+    uint2* const my_word = s_word + tid;
 
     // ---- stage tile k into buffer b: every warp derives the run table itself (two look-ups per lane + a shuffle scan),
     // then copies its own runs (boundaries + candidates).  No block-wide barrier inside.
@@ -327,6 +319,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                 int nw = 0;
                 while (k < NRUN) {
                     open_run(k);
+                    const int gb31 = s_gbeg[q_run] + 31;      // staged index -> global index (+ 31: the iterator counts leading zeros)
                     const int a4 = vs & ~3;
                     const int ng = (ve - a4 + 3) >> 2;
                     const int Tg = __reduce_max_sync(0xffffffffu, ve > vs ? ng : 0);   // the warp scans its longest range
@@ -362,8 +355,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                         m &= (unsigned)(0xFFFFFFFF00000000ull >> lim);
                         if (wc == 0) m &= 0xFFFFFFFFu >> (vs - a4);            // aligned-down head
                         if (m) {
-                            my_mask[nw * NT] = m;
-                            my_base[nw * NT] = (unsigned short)((q_run << 11) | j0);
+                            my_word[nw * NT] = make_uint2(m, (unsigned)(j0 + gb31));
                             ++nw;
                         }
                         ++wc;
@@ -371,67 +363,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                     if (full) break;
                     ++k; wc = 0;
                 }
-#ifdef PST_P2_OLD
-                // ---- phase 2: two hits per trip, j state gathered from global memory (L1/L2 hits), exact test, branch-free body
-                {
-                    // hit iterator over the mask words (none of them empty): m = bits left in the current word, base31 = global index
-                    // of its first candidate + 31, w = next word
-                    int w = 0, base31 = 0;
-                    unsigned m = 0;
-                    auto word_base = [&](int ww) { const int b16 = my_base[ww * NT]; return (b16 & 2047) + s_gbeg[b16 >> 11] + 31; };
-                    if (nw > 0 && DBG != 3) { m = my_mask[0]; base31 = word_base(0); w = 1; }
-                    if (DBG == 3) a.au += (R)nw;      // timing ablation: phase 1 only
-                    auto pop = [&]() -> int {      // requires m != 0
-                        const int msb = 31 - __clz(m);
-                        int j = base31 - msb;
-                        asm("" : "+r"(j));        // keep j a plain 32-bit value: the record index below is 32-bit arithmetic + one IMAD.WIDE
-                        m ^= 1u << msb;
-                        if (m == 0 && w < nw) { m = my_mask[w * NT]; base31 = word_base(w); ++w; }
-                        return j;
-                    };
-                    while (m != 0) {
-                        const int j0 = pop();
-                        const bool v1 = m != 0;
-                        const int j1 = v1 ? pop() : j0;
-                        R xj0, yj0, zj0, uj0, vj0, wj0, rj0, pj0, xj1, yj1, zj1, uj1, vj1, wj1, rj1, pj1, mj0 = A.m_uni, mj1 = A.m_uni;
-                        const R rc2 = UNI ? C.u_rc2 : I.rc2;
-                        if (DBG == 1) {     // timing ablation (wrong results): no gathers, the j state is made up from the index
-                            xj0 = I.x + (R)(j0 & 15) * (R)1e-3; yj0 = I.y + (R)(j0 & 7) * (R)1e-3; zj0 = I.z; uj0 = I.u; vj0 = I.v; wj0 = (R)j0; rj0 = I.rho; pj0 = I.por2;
-                            xj1 = I.x + (R)(j1 & 15) * (R)1e-3; yj1 = I.y + (R)(j1 & 7) * (R)1e-3; zj1 = I.z; uj1 = I.u; vj1 = I.v; wj1 = (R)j1; rj1 = I.rho; pj1 = I.por2;
-                        } else if (REC) {
-                            const P2* q0 = reinterpret_cast<const P2*>(A.rec) + rec_index(j0);
-                            const P2* q1 = reinterpret_cast<const P2*>(A.rec) + rec_index(j1);
-                            const P2 a0 = q0[0], b0 = q0[8], c0 = q0[16], d0 = q0[24], a1 = q1[0], b1 = q1[8], c1 = q1[16], d1 = q1[24];
-                            xj0 = a0.x; yj0 = a0.y; zj0 = b0.x; uj0 = b0.y; vj0 = c0.x; wj0 = c0.y; rj0 = d0.x; pj0 = d0.y;
-                            xj1 = a1.x; yj1 = a1.y; zj1 = b1.x; uj1 = b1.y; vj1 = c1.x; wj1 = c1.y; rj1 = d1.x; pj1 = d1.y;
-                            if (!UNI) { mj0 = q0[32].x; mj1 = q1[32].x; }
-                        } else {
-                            xj0 = A.x[j0]; yj0 = A.y[j0]; zj0 = DIM == 3 ? A.z[j0] : (R)0; uj0 = A.u[j0]; vj0 = A.v[j0]; wj0 = DIM == 3 ? A.w[j0] : (R)0;
-                            rj0 = A.rho[j0]; pj0 = A.por2[j0];
-                            xj1 = A.x[j1]; yj1 = A.y[j1]; zj1 = DIM == 3 ? A.z[j1] : (R)0; uj1 = A.u[j1]; vj1 = A.v[j1]; wj1 = DIM == 3 ? A.w[j1] : (R)0;
-                            rj1 = A.rho[j1]; pj1 = A.por2[j1];
-                            if (!UNI) { mj0 = A.m[j0]; mj1 = A.m[j1]; }
-                        }
-                        if (DBG == 2) {     // timing ablation (wrong results): gathers only, no pair body
-                            a.au += xj0 + yj0 + zj0 + uj0; a.av += vj0 + wj0 + rj0 + pj0; a2.au += xj1 + yj1 + zj1 + uj1; a2.av += vj1 + wj1 + rj1 + pj1;
-                            continue;
-                        }
-                        const R dx0 = I.x - xj0, dy0 = I.y - yj0, dz0 = DIM == 3 ? I.z - zj0 : (R)0;
-                        const R dx1 = I.x - xj1, dy1 = I.y - yj1, dz1 = DIM == 3 ? I.z - zj1 : (R)0;
-                        R r20 = dist2<DIM, R>(dx0, dy0, dz0), r21 = dist2<DIM, R>(dx1, dy1, dz1);
-                        const bool in0 = r20 < rc2 && r20 > (R)0;              // the exact test (the set is defined here)
-                        const bool in1 = v1 && r21 < rc2 && r21 > (R)0;
-                        r20 = in0 ? r20 : (R)1; r21 = in1 ? r21 : (R)1;
-                        R m0 = in0 ? mj0 : (R)0, m1 = in1 ? mj1 : (R)0;
-                        if (COUPLED) {   // signed SPH mass: the pair counts iff i or j is fluid
-                            m0 = (fluid_i || m0 > (R)0) ? fabs(m0) : (R)0;
-                            m1 = (fluid_i || m1 > (R)0) ? fabs(m1) : (R)0;
-                        }
-                        pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx0, dy0, dz0, r20, uj0, vj0, wj0, rj0, m0, pj0, a);
-                        pair_body<R, DIM, CONT, MOM, UNI>(C, I, dx1, dy1, dz1, r21, uj1, vj1, wj1, rj1, m1, pj1, a2);
-                    }
-                }
-#else
                 // ---- phase 2: one hit per body, software-pipelined -- the record of the NEXT hit is in flight while the body of
                 // the current one runs (two register sets, loop unrolled by two), so the L1 latency of the gathers hides behind
                 // ~40 FP64 instructions instead of stalling the warp at the head of every trip.  The loop is warp-uniform (runs
@@ -441,31 +372,26 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                 else {
                     // hit iterator over the mask words (none empty) with one word of lookahead: m = bits left in the current
                     // word, base31 = global index of its first candidate + 31; (mN, bN) = the next word, raw; w = the one after
-                    // All of it branch-free (predicated shared-memory loads), so the pipelined loop below is ONE basic block and ptxas
-                    // can hoist a pop and its gathers above the body that precedes them.
-                    const unsigned a_mask = (unsigned)__cvta_generic_to_shared(my_mask), a_base = (unsigned)__cvta_generic_to_shared(my_base);
-                    const unsigned a_gbeg = (unsigned)__cvta_generic_to_shared(s_gbeg);
-                    unsigned m = 0, mN = 0, b16 = 0;
-                    int base31 = 0, baseN = 0, w = 2;
-                    auto word_base = [&](unsigned b) { return (int)(b & 2047u) + s_gbeg[b >> 11] + 31; };
-                    if (nw > 0) { m = my_mask[0]; base31 = word_base(my_base[0]); }
-                    if (nw > 1) { mN = my_mask[NT]; baseN = word_base(my_base[NT]); }
+                    // All of it branch-free (one predicated 8-byte shared-memory load per word), so the pipelined loop below is ONE basic
+                    // block and ptxas can hoist a pop and its gathers above the body that precedes them.
+                    const unsigned a_word = (unsigned)__cvta_generic_to_shared(my_word);
+                    const unsigned pend = a_word + (unsigned)nw * (NT * 8);
+                    unsigned m = 0, mN = 0, base31 = 0, baseN = 0, pw = a_word + 2 * (NT * 8);
+                    if (nw > 0) { const uint2 w0 = my_word[0]; m = w0.x; base31 = w0.y; }
+                    if (nw > 1) { const uint2 w1 = my_word[NT]; mN = w1.x; baseN = w1.y; }
                     const int jdummy = s_ibeg[0];
                     auto pop = [&](bool& valid) -> int {
                         valid = m != 0;
                         const int c = __clz(m);
-                        int j = base31 - 31 + c;
-                        m &= 0x7fffffffu >> min(c, 31);
+                        int j = (int)base31 - 31 + c;
+                        m &= __funnelshift_rc(0x7fffffffu, 0u, c);      // clear the bit just taken (c = 32: nothing left anyway)
                         const bool adv = valid && m == 0;      // word exhausted: step to the preloaded one, preload the one after
-                        const bool ld = adv && w < nw;
+                        const bool ld = adv && pw < pend;
                         m = adv ? mN : m;
                         base31 = adv ? baseN : base31;
                         mN = adv ? 0u : mN;
-                        mN = lds_u32_if(a_mask + (unsigned)w * (NT * 4), ld, mN);
-                        b16 = lds_u16_if(a_base + (unsigned)w * (NT * 2), ld, b16);
-                        const unsigned gq = lds_u32_if(a_gbeg + ((b16 >> 11) << 2), ld, 0u);
-                        baseN = ld ? (int)(b16 & 2047u) + (int)gq + 31 : baseN;
-                        w += adv ? 1 : 0;
+                        lds_u64_if(pw, ld, mN, baseN);
+                        pw += adv ? (unsigned)(NT * 8) : 0u;
                         j = valid ? j : jdummy;
                         asm("" : "+r"(j));        // keep j a plain 32-bit value: the record index below is 32-bit arithmetic + one IMAD.WIDE
                         return j;
@@ -515,7 +441,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                         body(rB, vb);
                     }
                 }
-#endif
                 if (k == NRUN) break;      // warp-uniform
             }
             if (active) {
@@ -580,7 +505,7 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     double ppc = pst_param(ctx, "_ppc", 0.0);      // mean occupancy of the occupied COARSE cells (k_scan_tiles)
     if (!(ppc > 0)) ppc = DIM == 3 ? 14.0 : 6.0;
     ZTile T;
-    T.maxw = pst_option(ctx, "tile_words", 12);
+    T.maxw = pst_option(ctx, "tile_words", 10);
     // deepest tile (fine cells): twice the depth that holds one thread per particle at the mean occupancy, bounded by the f32
     // pre-filter (tile-local coordinates reach gf / S + 6 cells: <= 32 cells keeps the f32 error of r^2 below half of the 2^-15
     // margin, tests/test_prefilter_margin.py), by the boundary table and by the staging rows
@@ -628,7 +553,7 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     constexpr int kZRow = kZJcap + kZPad;
     const size_t tab_ints = (size_t)((D::NR + D::NR + 1 + D::NI + D::NI + 1 + 4 + NT / 32 + D::NR * T.wmax + 3) & ~3);
     constexpr int nbuf = NBUF;
-    const size_t smem = nbuf * tab_ints * sizeof(int) + (size_t)nbuf * (DIM == 3 ? 3 : 2) * kZRow * sizeof(float) + (size_t)T.maxw * NT * 6;
+    const size_t smem = nbuf * tab_ints * sizeof(int) + (size_t)nbuf * (DIM == 3 ? 3 : 2) * kZRow * sizeof(float) + (size_t)T.maxw * NT * 8;
     if (smem > 113 * 1024) return pst_fail(ctx, PST_EINVAL, "tile_words too large (%zu bytes of shared memory per CTA)", smem);
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
