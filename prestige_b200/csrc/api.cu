@@ -233,6 +233,8 @@ static pst_status check_flags(pst_ctx* ctx) {
     }
     if (ctx->h_flags[4]) {
         PST_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int32_t), ctx->stream));
+        ctx->nbrs_valid = false;        // the ghost rows and the ghost cell table are stale: nothing may be evaluated on them
+        ctx->eos_valid = false;
         return pst_fail(ctx, PST_ENCCL, "peer-memory halo: a slab neighbour did not publish its edge layers in time");
     }
     if (ctx->h_flags[2]) {
@@ -362,7 +364,8 @@ pst_status pst_set_option(pst_ctx* ctx, const char* name, int value) {
         {"force_kernel", 0, 3},          // WCSPH pair kernel: 0 gather | 1 warp per cell | 2 tiled lists | 3 tiled z-runs + bit masks
         {"dem_kernel", 0, 2},
         {"sort_impl", 0, 1},             // 0 library radix sort + bounds kernel (A/B) | 1 counting sort (default)
-        {"halo_impl", 0, 2},             // 0 per-array NCCL | 1 packed NCCL | 2 peer memory (default)
+        {"halo_impl", 0, 2},             // 0 per-array NCCL | 1 packed NCCL | 2 peer memory (default; falls back to 1 where the GPUs cannot map each other)
+        {"halo_timeout_ms", 0, 86400000},// peer-memory halo: how long a rank waits for its neighbour's step before PST_ENCCL (0 = for ever; default 10 min)
         {"uniform_mass", 0, 1},
         {"uniform_mass_global", 0, 1},
         {"tile_g", 0, 64},               // 0 = from the measured cell occupancy

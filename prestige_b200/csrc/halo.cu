@@ -30,12 +30,14 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclInt8 = 0 };
+enum { ncclInt8 = 0, ncclInt32 = 2 };
+enum { ncclMin = 3 };
 typedef ncclResult_t (*fn_GetUniqueId)(ncclUniqueId*);
 typedef ncclResult_t (*fn_CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
 typedef ncclResult_t (*fn_CommDestroy)(ncclComm_t);
 typedef ncclResult_t (*fn_Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef ncclResult_t (*fn_Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*fn_AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef ncclResult_t (*fn_Group)(void);
 typedef const char* (*fn_GetErrorString)(ncclResult_t);
 
@@ -46,6 +48,7 @@ struct NcclApi {
     fn_CommDestroy CommDestroy = nullptr;
     fn_Send Send = nullptr;
     fn_Recv Recv = nullptr;
+    fn_AllReduce AllReduce = nullptr;
     fn_Group GroupStart = nullptr, GroupEnd = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
     std::string err;
@@ -68,6 +71,7 @@ NcclApi* nccl_api() {
     PST_SYM(CommDestroy, "ncclCommDestroy")
     PST_SYM(Send, "ncclSend")
     PST_SYM(Recv, "ncclRecv")
+    PST_SYM(AllReduce, "ncclAllReduce")
     PST_SYM(GroupStart, "ncclGroupStart")
     PST_SYM(GroupEnd, "ncclGroupEnd")
     PST_SYM(GetErrorString, "ncclGetErrorString")
@@ -96,6 +100,7 @@ struct PstComm {
     char* p2p_send[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][parity]: MY receive buffers ([0] filled by the left neighbour)
     char* p2p_peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [0] = the left neighbour's buffer for what comes from ITS right (= me), [1] likewise
     size_t p2p_bytes = 0;
+    bool p2p_failed = false;       // a rank could not map its neighbour's buffer (no P2P / IPC): every rank uses the packed NCCL halo instead
     int epoch = 0;
 };
 
@@ -103,6 +108,15 @@ struct PstComm {
     do {                                                                                                     \
         ncclResult_t r__ = (expr);                                                                           \
         if (r__ != 0) return pst_fail(ctx, PST_ENCCL, "%s: %s", #expr, nccl_api()->GetErrorString(r__));     \
+    } while (0)
+// ... between ncclGroupStart and ncclGroupEnd: a failing call still closes the group before returning
+#define PST_NCCL_G(ctx, expr)                                                                                \
+    do {                                                                                                     \
+        ncclResult_t r__ = (expr);                                                                           \
+        if (r__ != 0) {                                                                                      \
+            nccl_api()->GroupEnd();                                                                          \
+            return pst_fail(ctx, PST_ENCCL, "%s: %s", #expr, nccl_api()->GetErrorString(r__));               \
+        }                                                                                                    \
     } while (0)
 
 namespace {
@@ -188,7 +202,7 @@ __global__ void k_halo_publish(int* flag_l, int* flag_r, int epoch) {
 // [-ext, 0), the right neighbour's the HEAD of its left window and lands on [n, n + ext).  No NCCL, no host round trip.
 __global__ void __launch_bounds__(256) k_halo_pull(HaloList L, int W, int n, int layer, int32_t* __restrict__ cell_start, size_t kR1,
                                                    const char* __restrict__ peer_l, const char* __restrict__ peer_r, size_t flag_off,
-                                                   int epoch, int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
+                                                   int epoch, long long timeout_clk, int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
     const int side = blockIdx.z, a = blockIdx.y;
     const char* buf = side == 0 ? peer_l : peer_r;
     if (!buf) return;
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(256) k_halo_pull(HaloList L, int W, int n, int
         const int* flag = reinterpret_cast<const int*>(buf + flag_off);
         const long long t0 = clock64();
         int seen = ld_acquire_sys(flag);
-        while (seen < epoch && clock64() - t0 < 6000000000ll && *(volatile int*)&flags[4] == 0) { __nanosleep(200); seen = ld_acquire_sys(flag); }
+        while (seen < epoch && (timeout_clk <= 0 || clock64() - t0 < timeout_clk) && *(volatile int*)&flags[4] == 0) { __nanosleep(200); seen = ld_acquire_sys(flag); }
         ok = seen >= epoch;
         if (!ok) atomicExch(&flags[4], 1);        // neighbour never published: reported as PST_ENCCL at the next sync
     }
@@ -219,6 +233,15 @@ __global__ void __launch_bounds__(256) k_halo_pull(HaloList L, int W, int n, int
     // loads bypass L1 (__ldcg): the neighbour rewrites this buffer over NVLink every second step
     if (L.esize[a] == 8) reinterpret_cast<unsigned long long*>(L.arr[a])[dst] = __ldcg(reinterpret_cast<const unsigned long long*>(buf + L.off[a]) + src);
     else reinterpret_cast<uint32_t*>(L.arr[a])[dst] = __ldcg(reinterpret_cast<const uint32_t*>(buf + L.off[a]) + src);
+}
+
+__global__ void k_set_flag(int32_t* p, int32_t v) { *p = v; }
+
+// migration: does this rank have room for what its neighbours send?  mine = (n_stay, n_stay + nL, n); a neighbour's triple
+// likewise -- the left one's right-leavers and the right one's left-leavers arrive here
+__global__ void k_mig_room(const int32_t* mine, const int32_t* from_l, const int32_t* from_r, int has_l, int has_r, long long capacity, int32_t* ok) {
+    const long long aL = has_l ? from_l[2] - from_l[1] : 0, aR = has_r ? from_r[1] - from_r[0] : 0;
+    *ok = (long long)mine[0] + aL + aR <= capacity;
 }
 
 std::vector<PstArray*> ghost_arrays(pst_ctx* ctx) {
@@ -332,17 +355,25 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
     // The three table entries (n_stay, n_stay + nL, n) go to both neighbours straight from device memory, then ONE
     // read-back + stream sync tells the host its own split and what arrives (was: sync, count hand-shake, sync).
     PST_NCCL(ctx, api->GroupStart());
-    if (left >= 0) { PST_NCCL(ctx, api->Send(ctx->cell_start + nc, 12, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 4, 12, ncclInt8, left, c->comm, ctx->stream)); }
-    if (right >= 0) { PST_NCCL(ctx, api->Send(ctx->cell_start + nc, 12, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 8, 12, ncclInt8, right, c->comm, ctx->stream)); }
+    if (left >= 0) { PST_NCCL_G(ctx, api->Send(ctx->cell_start + nc, 12, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL_G(ctx, api->Recv(c->d_counts + 4, 12, ncclInt8, left, c->comm, ctx->stream)); }
+    if (right >= 0) { PST_NCCL_G(ctx, api->Send(ctx->cell_start + nc, 12, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL_G(ctx, api->Recv(c->d_counts + 8, 12, ncclInt8, right, c->comm, ctx->stream)); }
     PST_NCCL(ctx, api->GroupEnd());
+    // Does everybody have room for its arrivals?  Decided on the device and combined over ALL ranks (one 4-byte all-reduce in
+    // the same stream), so either every rank posts the payload exchange below or none does: a rank that is full can never
+    // leave its neighbours waiting in a send that is not matched.
+    k_mig_room<<<1, 1, 0, ctx->stream>>>(ctx->cell_start + nc, c->d_counts + 4, c->d_counts + 8, left >= 0, right >= 0, (long long)ctx->capacity, c->d_counts + 14);
+    PST_NCCL(ctx, api->AllReduce(c->d_counts + 14, c->d_counts + 14, 1, ncclInt32, ncclMin, c->comm, ctx->stream));
     PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts, ctx->cell_start + nc, 3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 4, c->d_counts + 4, 8 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 4, c->d_counts + 4, 11 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int n_stay = c->h_counts[0], nL = c->h_counts[1] - c->h_counts[0], nR = c->h_counts[2] - c->h_counts[1];
     // what the left neighbour sends me is ITS right-leavers, and vice versa
     const int aL = left >= 0 ? c->h_counts[6] - c->h_counts[5] : 0, aR = right >= 0 ? c->h_counts[9] - c->h_counts[8] : 0;
-    if ((uint64_t)n_stay + aL + aR > ctx->capacity)
-        return pst_fail(ctx, PST_ENOMEM, "migration: %d stayers + %d arrivals exceed capacity %llu", n_stay, aL + aR, (unsigned long long)ctx->capacity);
+    if (!c->h_counts[14]) {
+        if ((uint64_t)n_stay + aL + aR > ctx->capacity)
+            return pst_fail(ctx, PST_ENOMEM, "migration: %d stayers + %d arrivals exceed capacity %llu", n_stay, aL + aR, (unsigned long long)ctx->capacity);
+        return pst_fail(ctx, PST_ENOMEM, "migration: another rank has no room for its arrivals (its capacity is exceeded); nothing was exchanged");
+    }
     if (nL + nR + aL + aR > 0) {
         PST_TRY(pst_resolve_history(ctx));   // contact-history rows travel with their particles: put them in the new order first
         PST_NCCL(ctx, api->GroupStart());
@@ -353,12 +384,12 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
                 char* cur = pst_ptr<char>(ctx, &a, r, a.cur);
                 char* alt = pst_ptr<char>(ctx, &a, r, 1 - a.cur);
                 if (left >= 0) {
-                    if (nL > 0) PST_NCCL(ctx, api->Send(cur + (size_t)n_stay * es, (size_t)nL * es, ncclInt8, left, c->comm, ctx->stream));
-                    if (aL > 0) PST_NCCL(ctx, api->Recv(alt, (size_t)aL * es, ncclInt8, left, c->comm, ctx->stream));
+                    if (nL > 0) PST_NCCL_G(ctx, api->Send(cur + (size_t)n_stay * es, (size_t)nL * es, ncclInt8, left, c->comm, ctx->stream));
+                    if (aL > 0) PST_NCCL_G(ctx, api->Recv(alt, (size_t)aL * es, ncclInt8, left, c->comm, ctx->stream));
                 }
                 if (right >= 0) {
-                    if (nR > 0) PST_NCCL(ctx, api->Send(cur + (size_t)(n_stay + nL) * es, (size_t)nR * es, ncclInt8, right, c->comm, ctx->stream));
-                    if (aR > 0) PST_NCCL(ctx, api->Recv(alt + (size_t)aL * es, (size_t)aR * es, ncclInt8, right, c->comm, ctx->stream));
+                    if (nR > 0) PST_NCCL_G(ctx, api->Send(cur + (size_t)(n_stay + nL) * es, (size_t)nR * es, ncclInt8, right, c->comm, ctx->stream));
+                    if (aR > 0) PST_NCCL_G(ctx, api->Recv(alt + (size_t)aL * es, (size_t)aR * es, ncclInt8, right, c->comm, ctx->stream));
                 }
             }
         }
@@ -378,36 +409,66 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
     return PST_OK;
 }
 
-// one-time setup of the peer-memory halo: allocate my double-buffered send windows, swap cudaIpc handles with the two
-// slab neighbours (the 64-byte handles travel by ncclSend/ncclRecv, once), map theirs.
-static pst_status p2p_setup(pst_ctx* ctx, size_t bytes, int left, int right) {
+// one-time setup of the peer-memory halo: allocate my double-buffered receive windows, swap cudaIpc handles with the two
+// slab neighbours (the 64-byte handles travel by ncclSend/ncclRecv, once), map theirs.  Whether that works is a property of
+// the machine (no P2P between the two GPUs, ranks in different IPC namespaces or on different nodes, threads of one process):
+// every rank tries, the outcomes are combined with ONE ncclAllReduce(min), and if any rank failed ALL ranks release what they
+// mapped and use the packed NCCL halo (halo_impl = 1) from then on -- a collective decision, so no rank waits on an epoch
+// word nobody will raise.  *use_p2p reports the outcome.
+static pst_status p2p_setup(pst_ctx* ctx, size_t bytes, int left, int right, bool* use_p2p) {
     PstComm* c = ctx->comm;
     NcclApi* api = nccl_api();
-    if (c->p2p_bytes >= bytes) return PST_OK;
+    *use_p2p = !c->p2p_failed;
+    if (c->p2p_failed || c->p2p_bytes >= bytes) return PST_OK;
     if (c->p2p_bytes != 0) return pst_fail(ctx, PST_ESTATE, "peer-memory halo: the message size changed after setup");
     cudaIpcMemHandle_t mine[2][2], theirs[2][2];
+    std::memset(mine, 0, sizeof mine);
     std::memset(theirs, 0, sizeof theirs);
-    for (int sd = 0; sd < 2; ++sd)
-        for (int par = 0; par < 2; ++par) {
-            if (cudaMalloc((void**)&c->p2p_send[sd][par], bytes) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "peer-memory halo buffers (%zu bytes)", bytes);
-            PST_CUDA(ctx, cudaMemsetAsync(c->p2p_send[sd][par], 0, bytes, ctx->stream));
-            PST_CUDA(ctx, cudaIpcGetMemHandle(&mine[sd][par], c->p2p_send[sd][par]));
+    int ok = 1;
+    for (int sd = 0; sd < 2 && ok; ++sd)
+        for (int par = 0; par < 2 && ok; ++par) {
+            if (cudaMalloc((void**)&c->p2p_send[sd][par], bytes) != cudaSuccess) { c->p2p_send[sd][par] = nullptr; ok = 0; break; }
+            if (cudaMemsetAsync(c->p2p_send[sd][par], 0, bytes, ctx->stream) != cudaSuccess) ok = 0;
+            if (cudaIpcGetMemHandle(&mine[sd][par], c->p2p_send[sd][par]) != cudaSuccess) ok = 0;
         }
+    cudaGetLastError();                                // a failed probe must not poison the context
     constexpr size_t HB = sizeof(cudaIpcMemHandle_t);
     char* d_h = nullptr;                               // [0..1] mine for the left, [2..3] mine for the right, [4..5] from left, [6..7] from right
-    PST_CUDA(ctx, cudaMalloc((void**)&d_h, 8 * HB));
+    PST_CUDA(ctx, cudaMalloc((void**)&d_h, 8 * HB + 16));
+    int32_t* d_ok = reinterpret_cast<int32_t*>(d_h + 8 * HB);
     PST_CUDA(ctx, cudaMemcpyAsync(d_h, mine, 4 * HB, cudaMemcpyHostToDevice, ctx->stream));
+    // the swap always runs (a rank whose allocation failed sends zeroed handles): the neighbours' receives must be matched
     PST_NCCL(ctx, api->GroupStart());
-    if (left >= 0) { PST_NCCL(ctx, api->Send(d_h, 2 * HB, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(d_h + 4 * HB, 2 * HB, ncclInt8, left, c->comm, ctx->stream)); }
-    if (right >= 0) { PST_NCCL(ctx, api->Send(d_h + 2 * HB, 2 * HB, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(d_h + 6 * HB, 2 * HB, ncclInt8, right, c->comm, ctx->stream)); }
+    if (left >= 0) { PST_NCCL_G(ctx, api->Send(d_h, 2 * HB, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL_G(ctx, api->Recv(d_h + 4 * HB, 2 * HB, ncclInt8, left, c->comm, ctx->stream)); }
+    if (right >= 0) { PST_NCCL_G(ctx, api->Send(d_h + 2 * HB, 2 * HB, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL_G(ctx, api->Recv(d_h + 6 * HB, 2 * HB, ncclInt8, right, c->comm, ctx->stream)); }
     PST_NCCL(ctx, api->GroupEnd());
     PST_CUDA(ctx, cudaMemcpyAsync(theirs, d_h + 4 * HB, 4 * HB, cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_h);
     // what the left neighbour sent me are the handles of ITS windows for its RIGHT neighbour (= me), and vice versa
-    for (int par = 0; par < 2; ++par) {
-        if (left >= 0) PST_CUDA(ctx, cudaIpcOpenMemHandle((void**)&c->p2p_peer[0][par], theirs[0][par], cudaIpcMemLazyEnablePeerAccess));
-        if (right >= 0) PST_CUDA(ctx, cudaIpcOpenMemHandle((void**)&c->p2p_peer[1][par], theirs[1][par], cudaIpcMemLazyEnablePeerAccess));
+    const bool forced_off = std::getenv("PST_P2P_DISABLE") != nullptr;     // (tests: exercise the fallback on a machine that has P2P)
+    for (int par = 0; par < 2 && ok; ++par) {
+        if (left >= 0 && (forced_off || cudaIpcOpenMemHandle((void**)&c->p2p_peer[0][par], theirs[0][par], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)) { c->p2p_peer[0][par] = nullptr; ok = 0; }
+        if (right >= 0 && ok && (forced_off || cudaIpcOpenMemHandle((void**)&c->p2p_peer[1][par], theirs[1][par], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)) { c->p2p_peer[1][par] = nullptr; ok = 0; }
+    }
+    cudaGetLastError();
+    // the collective decision
+    k_set_flag<<<1, 1, 0, ctx->stream>>>(d_ok, ok);
+    PST_NCCL(ctx, api->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, ctx->stream));
+    int all_ok = 0;
+    PST_CUDA(ctx, cudaMemcpyAsync(&all_ok, d_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    if (!all_ok) {
+        for (int sd = 0; sd < 2; ++sd)
+            for (int par = 0; par < 2; ++par) {
+                if (c->p2p_peer[sd][par]) cudaIpcCloseMemHandle(c->p2p_peer[sd][par]);
+                cudaFree(c->p2p_send[sd][par]);
+                c->p2p_peer[sd][par] = c->p2p_send[sd][par] = nullptr;
+            }
+        cudaGetLastError();
+        c->p2p_failed = true;
+        *use_p2p = false;
+        return PST_OK;
     }
     c->p2p_bytes = bytes;
     return PST_OK;
@@ -460,19 +521,27 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
             // ---- peer memory: the pack kernel stores this step's edge layers into the neighbours' parity buffers over
             // NVLink, a one-thread kernel raises the epoch words there, the unpack kernel waits for MY buffers' epoch
             const size_t flag_off = (msg + 15) & ~(size_t)15;
-            PST_TRY(p2p_setup(ctx, flag_off + 16, left, right));
+            bool use_p2p = true;
+            PST_TRY(p2p_setup(ctx, flag_off + 16, left, right, &use_p2p));
+            if (use_p2p) {
+            // how long the pull kernel waits for a neighbour's epoch word before it gives up (option halo_timeout_ms, default
+            // 10 minutes, 0 = for ever): rank skew of seconds is normal (checkpoint or VTK output on one rank, first-call allocation)
+            static int clk_khz = 0;
+            if (!clk_khz) cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, ctx->cfg.device);
+            const long long timeout_clk = (long long)pst_option(ctx, "halo_timeout_ms", 600000) * (long long)std::max(clk_khz, 1000000);
             const int e = ++c->epoch, par = e & 1;
             PST_LAUNCH(ctx, k_halo_pack, grid, 256, 0, L, W, n, layer, ctx->cell_start, kL0, kR0, c->p2p_peer[0][par], c->p2p_peer[1][par], left >= 0, right >= 0, 1);
             PST_LAUNCH(ctx, k_halo_publish, 1, 1, 0, left >= 0 ? (int*)(c->p2p_peer[0][par] + flag_off) : nullptr,
                        right >= 0 ? (int*)(c->p2p_peer[1][par] + flag_off) : nullptr, e);
             PST_CUDA(ctx, cudaMemsetAsync(c->d_counts + 12, 0, 2 * 4, ctx->stream));
             PST_LAUNCH(ctx, k_halo_pull, grid, 256, 0, L, W, n, layer, ctx->cell_start, kR1, left >= 0 ? (const char*)c->p2p_send[0][par] : nullptr,
-                       right >= 0 ? (const char*)c->p2p_send[1][par] : nullptr, flag_off, e, c->d_counts, ctx->d_flags);
+                       right >= 0 ? (const char*)c->p2p_send[1][par] : nullptr, flag_off, e, timeout_clk, c->d_counts, ctx->d_flags);
             ctx->n_ghost_l = left >= 0 ? W : 0;
             ctx->n_ghost_r = right >= 0 ? W : 0;
             ctx->ghost_exact = false;
             ctx->eos_valid = false; ctx->state_epoch++;
             return PST_OK;
+            }      // (no peer access on this machine: fall through to the packed NCCL message)
         }
         if (c->msg_bytes < msg) {
             PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -487,12 +556,12 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
         PST_LAUNCH(ctx, k_halo_pack, grid, 256, 0, L, W, n, layer, ctx->cell_start, kL0, kR0, c->send_buf[0], c->send_buf[1], left >= 0, right >= 0, 0);
         PST_NCCL(ctx, api->GroupStart());
         if (left >= 0) {
-            PST_NCCL(ctx, api->Send(c->send_buf[0], msg, ncclInt8, left, c->comm, ctx->stream));
-            PST_NCCL(ctx, api->Recv(c->recv_buf[0], msg, ncclInt8, left, c->comm, ctx->stream));
+            PST_NCCL_G(ctx, api->Send(c->send_buf[0], msg, ncclInt8, left, c->comm, ctx->stream));
+            PST_NCCL_G(ctx, api->Recv(c->recv_buf[0], msg, ncclInt8, left, c->comm, ctx->stream));
         }
         if (right >= 0) {
-            PST_NCCL(ctx, api->Send(c->send_buf[1], msg, ncclInt8, right, c->comm, ctx->stream));
-            PST_NCCL(ctx, api->Recv(c->recv_buf[1], msg, ncclInt8, right, c->comm, ctx->stream));
+            PST_NCCL_G(ctx, api->Send(c->send_buf[1], msg, ncclInt8, right, c->comm, ctx->stream));
+            PST_NCCL_G(ctx, api->Recv(c->recv_buf[1], msg, ncclInt8, right, c->comm, ctx->stream));
         }
         PST_NCCL(ctx, api->GroupEnd());
         PST_CUDA(ctx, cudaMemsetAsync(c->d_counts + 12, 0, 2 * 4, ctx->stream));
@@ -518,14 +587,21 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
     PST_CUDA(ctx, cudaMemcpyAsync(c->d_counts, c->h_counts, 4 * 4, cudaMemcpyHostToDevice, ctx->stream));
     // 2. counts
     PST_NCCL(ctx, api->GroupStart());
-    if (left >= 0) { PST_NCCL(ctx, api->Send(c->d_counts + 0, 4, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 2, 4, ncclInt8, left, c->comm, ctx->stream)); }
-    if (right >= 0) { PST_NCCL(ctx, api->Send(c->d_counts + 1, 4, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL(ctx, api->Recv(c->d_counts + 3, 4, ncclInt8, right, c->comm, ctx->stream)); }
+    if (left >= 0) { PST_NCCL_G(ctx, api->Send(c->d_counts + 0, 4, ncclInt8, left, c->comm, ctx->stream)); PST_NCCL_G(ctx, api->Recv(c->d_counts + 2, 4, ncclInt8, left, c->comm, ctx->stream)); }
+    if (right >= 0) { PST_NCCL_G(ctx, api->Send(c->d_counts + 1, 4, ncclInt8, right, c->comm, ctx->stream)); PST_NCCL_G(ctx, api->Recv(c->d_counts + 3, 4, ncclInt8, right, c->comm, ctx->stream)); }
     PST_NCCL(ctx, api->GroupEnd());
     PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 2, c->d_counts + 2, 2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int nL = left >= 0 ? c->h_counts[2] : 0, nR = right >= 0 ? c->h_counts[3] : 0;
-    if ((uint64_t)nL > ctx->ghost_cap || (uint64_t)nR > ctx->ghost_cap)
-        return pst_fail(ctx, PST_ENOMEM, "ghost layer of %d / %d particles exceeds ghost_capacity %llu", nL, nR, (unsigned long long)ctx->ghost_cap);
+    {   // every rank posts the payload group below or none does (a rank that is over capacity must not leave unmatched sends behind)
+        const int room = (uint64_t)nL <= ctx->ghost_cap && (uint64_t)nR <= ctx->ghost_cap;
+        k_set_flag<<<1, 1, 0, ctx->stream>>>(c->d_counts + 14, room);
+        PST_NCCL(ctx, api->AllReduce(c->d_counts + 14, c->d_counts + 14, 1, ncclInt32, ncclMin, c->comm, ctx->stream));
+        PST_CUDA(ctx, cudaMemcpyAsync(c->h_counts + 14, c->d_counts + 14, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!room) return pst_fail(ctx, PST_ENOMEM, "ghost layer of %d / %d particles exceeds ghost_capacity %llu", nL, nR, (unsigned long long)ctx->ghost_cap);
+        if (!c->h_counts[14]) return pst_fail(ctx, PST_ENOMEM, "halo: another rank's ghost layer exceeds its ghost_capacity; nothing was exchanged");
+    }
     const int n = (int)ctx->n;
     // 3. particles + cell-table slices, one NCCL group
     PST_NCCL(ctx, api->GroupStart());
@@ -533,22 +609,22 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
         char* base = pst_ptr<char>(ctx, a);
         const size_t es = a->esize;
         if (left >= 0) {
-            if (sL1 > sL0) PST_NCCL(ctx, api->Send(base + (ptrdiff_t)sL0 * es, (size_t)(sL1 - sL0) * es, ncclInt8, left, c->comm, ctx->stream));
-            if (nL > 0) PST_NCCL(ctx, api->Recv(base - (ptrdiff_t)nL * es, (size_t)nL * es, ncclInt8, left, c->comm, ctx->stream));
+            if (sL1 > sL0) PST_NCCL_G(ctx, api->Send(base + (ptrdiff_t)sL0 * es, (size_t)(sL1 - sL0) * es, ncclInt8, left, c->comm, ctx->stream));
+            if (nL > 0) PST_NCCL_G(ctx, api->Recv(base - (ptrdiff_t)nL * es, (size_t)nL * es, ncclInt8, left, c->comm, ctx->stream));
         }
         if (right >= 0) {
-            if (sR1 > sR0) PST_NCCL(ctx, api->Send(base + (ptrdiff_t)sR0 * es, (size_t)(sR1 - sR0) * es, ncclInt8, right, c->comm, ctx->stream));
-            if (nR > 0) PST_NCCL(ctx, api->Recv(base + (ptrdiff_t)n * es, (size_t)nR * es, ncclInt8, right, c->comm, ctx->stream));
+            if (sR1 > sR0) PST_NCCL_G(ctx, api->Send(base + (ptrdiff_t)sR0 * es, (size_t)(sR1 - sR0) * es, ncclInt8, right, c->comm, ctx->stream));
+            if (nR > 0) PST_NCCL_G(ctx, api->Recv(base + (ptrdiff_t)n * es, (size_t)nR * es, ncclInt8, right, c->comm, ctx->stream));
         }
     }
     const size_t tab_bytes = ((size_t)layer + 1) * 4;
     if (left >= 0) {
-        PST_NCCL(ctx, api->Send(ctx->cell_start + kL0, tab_bytes, ncclInt8, left, c->comm, ctx->stream));
-        PST_NCCL(ctx, api->Recv(c->d_tab_l, tab_bytes, ncclInt8, left, c->comm, ctx->stream));
+        PST_NCCL_G(ctx, api->Send(ctx->cell_start + kL0, tab_bytes, ncclInt8, left, c->comm, ctx->stream));
+        PST_NCCL_G(ctx, api->Recv(c->d_tab_l, tab_bytes, ncclInt8, left, c->comm, ctx->stream));
     }
     if (right >= 0) {
-        PST_NCCL(ctx, api->Send(ctx->cell_start + kR0, tab_bytes, ncclInt8, right, c->comm, ctx->stream));
-        PST_NCCL(ctx, api->Recv(c->d_tab_r, tab_bytes, ncclInt8, right, c->comm, ctx->stream));
+        PST_NCCL_G(ctx, api->Send(ctx->cell_start + kR0, tab_bytes, ncclInt8, right, c->comm, ctx->stream));
+        PST_NCCL_G(ctx, api->Recv(c->d_tab_r, tab_bytes, ncclInt8, right, c->comm, ctx->stream));
     }
     PST_NCCL(ctx, api->GroupEnd());
     // 4. splice the ghost layers into the cell table

@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_halo_exchange_matches_single_domain(world, tmp_path):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -44,7 +44,7 @@ def test_halo_exchange_matches_single_domain(world, tmp_path):
     assert tot == d["n_whole"]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_migration_matches_single_gpu(world, tmp_path):
     """pst_step across slab faces: particles (and everything they carry) migrate to the neighbour rank; the final state
     equals the single-GPU run particle by particle (matched by global id), and no particle is lost or duplicated."""
