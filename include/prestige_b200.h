@@ -184,7 +184,12 @@ PST_API pst_status pst_bodies_restore(pst_ctx* ctx);
  * pst_bodies_setup and only written when a checkpoint is restored). */
 PST_API pst_status pst_bodies_state(pst_ctx* ctx, const char* name, double* host, size_t n, int write);
 
-/* ---- multi-GPU: slab decomposition along x, ghost layers by NCCL send/recv ----------------- */
+/* ---- multi-GPU: slab decomposition along x ------------------------------------------------------------------
+ * One context per rank.  Ghost layers travel by peer-memory stores over NVLink (cudaIpc windows + an epoch word; option
+ * halo_impl = 2, the default) where the GPUs can map each other's memory -- probed once and agreed over all ranks -- and as
+ * one packed ncclSend/ncclRecv message per neighbour (halo_impl = 1) otherwise; halo_impl = 0 is the exact per-array NCCL
+ * exchange.  Particles that leave the slab migrate to the neighbour rank inside pst_build_neighbours (NCCL).  With a
+ * communicator attached host transfers are in DEVICE order and `id` is a caller-supplied global label. */
 #define PST_COMM_ID_BYTES 128
 PST_API pst_status pst_comm_unique_id(void* id_bytes /* PST_COMM_ID_BYTES */);
 /* rank r owns global cell layers [ix_lo, ix_hi) of the cfg box; neighbours are r-1 and r+1 */

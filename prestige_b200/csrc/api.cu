@@ -206,6 +206,7 @@ void pst_destroy(pst_ctx* ctx) {
     cudaFree(ctx->cell_start); cudaFree(ctx->sort_tmp); cudaFree(ctx->scan_sums); cudaFree(ctx->nf_pos); cudaFree(ctx->nf_idx); cudaFree(ctx->nf_rec); cudaFree(ctx->wp_pos); cudaFree(ctx->wp_idx); cudaFree(ctx->rec); cudaFree(ctx->ztiles); cudaFree(ctx->d_ztile_count); cudaFree(ctx->d_uni); cudaFree(ctx->stage); cudaFree(ctx->d_flags); cudaFree(ctx->d_bodies); cudaFree(ctx->d_body_start); cudaFree(ctx->d_body_vals);
     cudaFree(ctx->d_counters);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
+    if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_uni) cudaFreeHost(ctx->h_uni);
@@ -598,24 +599,91 @@ pst_status pst_integrate(pst_ctx* ctx, double dt) {
     return PST_OK;
 }
 
+static pst_status step_once(pst_ctx* ctx, double dt) {
+    PST_TRY(pst_nnps_build(ctx));
+    if (ctx->comm) PST_TRY(pst_halo_exchange(ctx));
+    if (ctx->cfg.physics & PST_PHYS_WCSPH) {
+        PST_TRY(pst_wcsph_eos(ctx));
+        if (pst_param(ctx, "boundary_model", 0.0) == 1.0) PST_TRY(pst_wcsph_wall_pressure(ctx));
+        PST_TRY(pst_wcsph_forces(ctx, true, true));
+    }
+    if (ctx->cfg.physics & PST_PHYS_DEM) {
+        ctx->params["dt"] = dt;
+        PST_TRY(pst_dem_forces(ctx));
+    }
+    return pst_integrate(ctx, dt);
+}
+
+// everything the captured launch sequence depends on besides the device data: particle count, time step, every parameter and
+// option, the set of arrays.  A change of any of them re-captures.
+static uint64_t step_graph_key(pst_ctx* ctx, double dt) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    mix(&ctx->n, sizeof ctx->n); mix(&dt, sizeof dt);
+    for (const auto& kv : ctx->params) { if (kv.first == "_ppc" || kv.first == "dt") continue; mix(kv.first.data(), kv.first.size()); mix(&kv.second, sizeof kv.second); }
+    for (const auto& kv : ctx->options) { mix(kv.first.data(), kv.first.size()); mix(&kv.second, sizeof kv.second); }
+    const size_t na = ctx->arrays.size();
+    mix(&na, sizeof na);
+    mix(&ctx->grid.sub, sizeof ctx->grid.sub);
+    return h ? h : 1;
+}
+
+// which buffer of every double-buffered array is current: the captured pointers are only right for the parity they were
+// captured at (every step flips them once; two steps restore them)
+static uint64_t buffer_parity(pst_ctx* ctx) {
+    uint64_t h = 1469598103934665603ull;
+    for (const auto& a : ctx->arrays) { h ^= (uint64_t)(a.cur + 1); h *= 1099511628211ull; }
+    return h;
+}
+
 pst_status pst_step(pst_ctx* ctx, double dt, int n_steps) {
     PstRange range("pst_step");
     if (!ctx || n_steps < 0) return PST_EINVAL;
     PST_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    for (int k = 0; k < n_steps; ++k) {
-        PST_TRY(pst_nnps_build(ctx));
-        if (ctx->comm) PST_TRY(pst_halo_exchange(ctx));
-        if (ctx->cfg.physics & PST_PHYS_WCSPH) {
-            PST_TRY(pst_wcsph_eos(ctx));
-            if (pst_param(ctx, "boundary_model", 0.0) == 1.0) PST_TRY(pst_wcsph_wall_pressure(ctx));
-            PST_TRY(pst_wcsph_forces(ctx, true, true));
+    int k = 0;
+    // Launch-bound contexts (the 2D dam break: ~20 launches of a few microseconds each per step) run pst_step as a CUDA graph:
+    // option graph = 1, single GPU, no rigid bodies.  Steps 1-2 of a sequence run eagerly (they allocate and tune), the next
+    // two are captured, every further pair is one cudaGraphLaunch.
+    const bool want_graph = pst_option(ctx, "graph", 0) == 1 && !ctx->comm && !ctx->d_bodies && ctx->n > 0 && n_steps >= 2;
+    if (want_graph) {
+        const uint64_t key = step_graph_key(ctx, dt);
+        if (ctx->step_graph && (ctx->step_graph_key != key || ctx->uni_dirty)) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
+        if (ctx->step_graph && buffer_parity(ctx) != ctx->step_graph_parity) {     // an odd number of eager steps since the capture: one more realigns
+            PST_TRY(step_once(ctx, dt));
+            ++k;
+            if (buffer_parity(ctx) != ctx->step_graph_parity) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
         }
-        if (ctx->cfg.physics & PST_PHYS_DEM) {
-            ctx->params["dt"] = dt;
-            PST_TRY(pst_dem_forces(ctx));
+        if (!ctx->step_graph && n_steps - k >= 4) {
+            for (int w = 0; w < 2; ++w, ++k) PST_TRY(step_once(ctx, dt));
+            ctx->step_graph_parity = buffer_parity(ctx);
+            const uint64_t l0 = ctx->launches;
+            cudaGraph_t g = nullptr;
+            PST_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+            ctx->capturing = true;
+            pst_status st = step_once(ctx, dt);
+            if (st == PST_OK) st = step_once(ctx, dt);
+            ctx->capturing = false;
+            const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+            if (st != PST_OK) { if (g) cudaGraphDestroy(g); return st; }
+            PST_CUDA(ctx, ce);
+            PST_CUDA(ctx, cudaGraphInstantiate(&ctx->step_graph, g, 0));
+            cudaGraphDestroy(g);
+            ctx->step_graph_key = key;
+            ctx->step_graph_launches = ctx->launches - l0;
+            ctx->launches = l0;                                   // nothing ran during the capture
+            // (the host-side state now describes "two steps later" although the device has not run them: the first replay
+            // below makes that true)
+            PST_CUDA(ctx, cudaGraphLaunch(ctx->step_graph, ctx->stream));
+            ctx->launches += ctx->step_graph_launches;
+            k += 2;
         }
-        PST_TRY(pst_integrate(ctx, dt));
+        if (ctx->step_graph)
+            for (; k + 2 <= n_steps; k += 2) {
+                PST_CUDA(ctx, cudaGraphLaunch(ctx->step_graph, ctx->stream));
+                ctx->launches += ctx->step_graph_launches;
+            }
     }
+    for (; k < n_steps; ++k) PST_TRY(step_once(ctx, dt));
     return PST_OK;
 }
 

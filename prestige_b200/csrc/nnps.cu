@@ -403,7 +403,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     ctx->n_ghost_l = ctx->n_ghost_r = 0;
     ctx->ghost_exact = true;
     // occupied-cell count of the PREVIOUS build (read back asynchronously; the very first build waits once)
-    if (ctx->stats_pending) {
+    if (ctx->stats_pending && !ctx->capturing) {
         PST_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
         ctx->stats_pending = false;
         if (ctx->h_counters[2] > 0) ctx->params["_ppc"] = (double)ctx->h_counters[3] / (double)ctx->h_counters[2];
@@ -434,11 +434,13 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
         }
         PST_LAUNCH(ctx, k_bounds, blocks_for((size_t)n + 1), kThreads, 0, n, nkeys, ctx->keys_out, ctx->cell_start, ctx->d_counters);
     }
-    PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    PST_CUDA(ctx, cudaEventRecord(ctx->ev_stats, ctx->stream));
-    ctx->h_counters[3] = (unsigned long long)n;
-    ctx->stats_pending = true;
-    if (ctx->params.find("_ppc") == ctx->params.end()) {   // first build: one-time wait so the first force pass is tuned too
+    if (!ctx->capturing) {     // (a captured step keeps the occupancy figure of the steps before it)
+        PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PST_CUDA(ctx, cudaEventRecord(ctx->ev_stats, ctx->stream));
+        ctx->h_counters[3] = (unsigned long long)n;
+        ctx->stats_pending = true;
+    }
+    if (!ctx->capturing && ctx->params.find("_ppc") == ctx->params.end()) {   // first build: one-time wait so the first force pass is tuned too
         PST_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
         ctx->stats_pending = false;
         if (ctx->h_counters[2] > 0) ctx->params["_ppc"] = (double)n / (double)ctx->h_counters[2];

@@ -106,6 +106,12 @@ struct pst_ctx {
     const void* contact_kernel_fn = nullptr;
     cudaEvent_t ev_stats = nullptr;  // completion of the async read-back of d_counters (occupied cells)
     bool stats_pending = false;
+    // pst_step as a CUDA graph (option graph = 1, single-GPU contexts): TWO consecutive steps captured once -- the double-buffered
+    // arrays are back on their original buffers after two flips, so the captured pointers stay valid -- and replayed
+    cudaGraphExec_t step_graph = nullptr;
+    uint64_t step_graph_key = 0, step_graph_parity = 0;
+    uint64_t step_graph_launches = 0;      // kernel launches one replay stands for
+    bool capturing = false;                // no host round trips while the stream is being captured
     PstComm* comm = nullptr;
     // multi-particle rigid bodies (rigid.cu): per-body records, field-major (rigid_core.h RbField), always double
     uint32_t n_bodies = 0;

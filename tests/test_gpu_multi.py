@@ -85,3 +85,21 @@ def test_coupled_sph_dem_across_slabs(world, tmp_path):
         for k, e in d["err"].items():
             assert e <= 1e-9, f"rank {rank} {k}: {e:.3e}"
     assert moved >= 2 and contacts > 0
+
+
+def test_halo_falls_back_without_peer_access(tmp_path):
+    """A machine whose GPUs cannot map each other's memory (no P2P, separate IPC namespaces): the peer-memory halo must detect
+    it at set-up, agree on it over all ranks and use the packed NCCL message instead -- same results, no hang.
+    PST_P2P_DISABLE makes every rank's probe fail."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(tmp_path), "halo"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PST_P2P_DISABLE="1"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for rank in range(2):
+        d = json.load(open(tmp_path / f"rank{rank}.json"))
+        for variant, errs in d["err"].items():
+            errs.pop("ghosts")
+            for k, e in errs.items():
+                assert e <= 1e-10, f"rank {rank} kernel variant {variant} {k}: {e:.3e}"
