@@ -35,7 +35,12 @@ struct ZTile {
 };
 
 constexpr int kZPad = 64;      // readable slack behind the staged rows: lanes with a short range over-scan with the warp
-template <int NT> constexpr int zjcap() { return NT >= 256 ? 1536 : 1024; }   // staged candidates per buffer (12 B each)
+// Tiles of up to kZRounds x NT particles (every warp evaluates kZRounds rows of 32 per tile) with ONE staging buffer: fewer tiles,
+// fewer barriers and table set-ups, and a better ratio of staged candidates to own particles (4.8 instead of 5.7) than
+// NT-particle tiles with two buffers in the same shared memory: 5.04 -> 4.92 ms at 10 M, L1 hit rate unchanged at 90 %
+// (profiles/r2_exp_log.txt).
+constexpr int kZRounds = 2, kZNbuf = 1;
+template <int NT> constexpr int zjcap() { return NT >= 256 ? 2560 : 1024; }   // staged candidates per buffer (12 B each)
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
 
@@ -450,6 +455,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
         }
     };
 
+
     // ---- persistent loop over this CTA's tiles, staging one tile ahead
     // tiles are handed out dynamically (one atomic per tile, fetched two iterations ahead by thread 0 and published through
     // shared memory at the barrier in between): neighbours in the list are evaluated at about the same time by different SMs
@@ -510,7 +516,7 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     // pre-filter (tile-local coordinates reach gf / S + 6 cells: <= 32 cells keeps the f32 error of r^2 below half of the 2^-15
     // margin, tests/test_prefilter_margin.py), by the boundary table and by the staging rows
     const int user_G = pst_option(ctx, "tile_g", 0) * S + pst_option(ctx, "tile_gf", 0);   // tile_g in COARSE cells, tile_gf in fine cells
-    int gfcap = user_G > 0 ? user_G : (int)std::ceil(2.0 * NT * S / (D::NI * ppc));
+    int gfcap = user_G > 0 ? user_G : (int)std::ceil(2.0 * NT * kZRounds * S / (D::NI * ppc));
     gfcap = std::min(std::max(gfcap, 1), std::max(1, nf));
     gfcap = std::min(gfcap, kMaxTileG * S);
     while (gfcap > 1 && D::NR * (gfcap + 2 * S + 1) > 2048) --gfcap;
@@ -519,7 +525,7 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     T.jcap = std::min(kZJcap, std::max(0, pst_option(ctx, "tile_jcap", kZJcap)));
     // ---- the tile list (device side; rebuilt when the cell table or the cut parameters changed)
     const int tiles_x = (g.n[0] + TA - 1) / TA, tiles_y = DIM == 3 ? (g.n[1] + D::BB - 1) / D::BB : 1;
-    const int target = user_G > 0 ? 0x3fffffff : NT;       // a forced depth (tests) cuts by depth alone
+    const int target = user_G > 0 ? 0x3fffffff : NT * kZRounds;       // a forced depth (tests) cuts by depth alone
     const size_t cap = (size_t)tiles_x * tiles_y * nf;     // a tile holds at least one fine cell: the list cannot overflow
     if (cap > ctx->ztiles_cap) {
         PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -584,5 +590,5 @@ template <class R, int DIM>
 pst_status launch_zrun(pst_ctx* ctx, bool cont, bool mom) {
     // two CTAs of 256 threads per SM, two staging buffers.  Measured and dropped (profiles/r2_exp_log.txt): one staging buffer
     // (+2 %), four CTAs of 128 threads with one or two buffers (+8 %)
-    return launch_zrun_shape<R, DIM, 256, 2>(ctx, cont, mom);
+    return launch_zrun_shape<R, DIM, 256, kZNbuf>(ctx, cont, mom);
 }
