@@ -344,13 +344,14 @@ def traffic_for(kernel_mangled: str, workload: str, real: str):
     `ncu --set full` capture).  Keyed by the MANGLED kernel symbol: an entry for another instantiation never matches."""
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(tp):
-        return None, "no profiles/traffic.json"
+        return None, "no profiles/traffic.json", None
     with open(tp) as f:
         t = json.load(f)
     for e in t.get("entries", []):
         if e.get("kernel_mangled") == kernel_mangled and e.get("workload") == workload and e.get("real") == real:
-            return e.get("dram_bytes_per_launch"), e.get("source")
-    return None, "no ncu capture of this kernel instantiation on this workload (profiles/traffic.json holds others)"
+            return e.get("dram_bytes_per_launch"), e.get("source"), {k: e.get(k) for k in ("l1_data_pipe_pct_of_peak", "fp64_pipe_pct_of_peak", "dram_pct_of_peak",
+                                                                                             "l1_hit_rate_pct", "l2_hit_rate_pct", "kernel_ms_under_ncu")}
+    return None, "no ncu capture of this kernel instantiation on this workload (profiles/traffic.json holds others)", None
 
 
 def parity_check(ctx, block, slab, rank, world, dist, torch):
@@ -619,9 +620,11 @@ def run_gpu(workload, args, rank, world, local_rank, torch, dist, *, steps, warm
     n_local = n
     t_kernel = t_force if block.physics != "dem" else t_force
     ach = b_force * n_local / t_kernel / 1e9
-    traffic, traffic_src = traffic_for(kern_mangled, workload, args.real)
+    traffic, traffic_src, ncu_units = traffic_for(kern_mangled, workload, args.real)
     roofline = {"bound": "hbm", "kernel": kern, "kernel_mangled": kern_mangled, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
+                # the unit this kernel actually sits on (recorded ncu capture of the SAME instantiation, not a live measurement)
+                "ncu_units": ncu_units,
                 "peak_source": peak_src, "alg_bytes_per_particle": b_force, "particles_per_launch": n_local,
                 "kernel_ms": t_kernel * 1e3,
                 "step": {"alg_bytes_per_particle": b_step, "achieved": b_step * n_total / (t_max / steps) / 1e9 / world,

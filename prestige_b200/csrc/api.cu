@@ -89,7 +89,7 @@ pst_status pst_grid_finalize(pst_ctx* ctx) {
 
 // m and h decide which pair kernel runs (uniform values become constants); whoever may have changed them marks the check stale
 static void note_uniform_dirty(pst_ctx* ctx, const PstArray* a) {
-    if (a->name == "m" || a->name == "h") ctx->uni_dirty = true;
+    if (a->name == "m" || a->name == "h" || a->name == "rad") ctx->uni_dirty = true;
 }
 
 static pst_status array_create(pst_ctx* ctx, const char* name, int dtype, uint32_t flags, int rows) {

@@ -388,6 +388,7 @@ pst_status launch_dem_integrate(pst_ctx* ctx, double dt) {
 
 pst_status pst_dem_forces(pst_ctx* ctx) {
     if (ctx->n == 0) return PST_OK;
+    PST_TRY(pst_check_cell_size(ctx));
     PST_TRY(PST_DISPATCH(ctx, launch_dem, ctx));
     ctx->contact_kernel_fn = ctx->last_kernel_fn;      // (the contact kernel is the last launch of the pass)
     return PST_OK;

@@ -96,6 +96,7 @@ struct pst_ctx {
     // every owned particle has the same mass / smoothing length (decided on the device, pst_uniform_refresh): the tiled
     // pair kernels then take them as constants instead of gathering m[j] and carrying the h-derived terms in registers
     bool m_uniform = false, h_uniform = false;
+    double h_max = 0.0, rad_max = 0.0;   // largest smoothing length / radius of the owned particles (pst_uniform_refresh)
     double m_value = 0.0, h_value = 0.0;
     bool uni_dirty = true;           // m or h may have changed since the last check (upload, pst_array pointer, new particle set)
     unsigned long long *d_uni = nullptr, *h_uni = nullptr;   // min / max bit patterns of m and h (device, pinned mirror)
@@ -188,6 +189,7 @@ pst_status pst_wcsph_wall_pressure(pst_ctx* ctx);                         // dum
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum);
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu
+pst_status pst_check_cell_size(pst_ctx* ctx);                             // wcsph.cu: cell_size >= kfac max(h), >= 2 max(rad)
 pst_status pst_dem_integrate(pst_ctx* ctx, double dt);
 pst_status pst_coupled_integrate(pst_ctx* ctx, double dt);                // wcsph.cu
 pst_status pst_rb_reduce(pst_ctx* ctx);                                   // rigid.cu: per-particle forces -> body force / torque

@@ -28,18 +28,21 @@ inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t)
 // Are the masses / smoothing lengths of the owned particles all equal?  min and max of the BIT PATTERNS (any total order
 // does: all equal <=> min == max), one atomic pair per block.
 template <class R>
-__global__ void __launch_bounds__(256) k_uniform_check(int n, const R* __restrict__ m, const R* __restrict__ h, unsigned long long* __restrict__ out) {
-    unsigned long long lo_m = ~0ull, hi_m = 0, lo_h = ~0ull, hi_h = 0;
+__global__ void __launch_bounds__(256) k_uniform_check(int n, const R* __restrict__ m, const R* __restrict__ h, const R* __restrict__ rad,
+                                                       unsigned long long* __restrict__ out) {
+    unsigned long long lo_m = ~0ull, hi_m = 0, lo_h = ~0ull, hi_h = 0, hi_r = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const unsigned long long km = (unsigned long long)__double_as_longlong((double)m[s]);
         const unsigned long long kh = h ? (unsigned long long)__double_as_longlong((double)h[s]) : 0ull;
         lo_m = min(lo_m, km); hi_m = max(hi_m, km); lo_h = min(lo_h, kh); hi_h = max(hi_h, kh);
+        if (rad) hi_r = max(hi_r, (unsigned long long)__double_as_longlong(fabs((double)rad[s])));     // (largest radius: the cell-size precondition)
     }
     for (int d = 16; d > 0; d >>= 1) {
         lo_m = min(lo_m, __shfl_xor_sync(0xffffffffu, lo_m, d)); hi_m = max(hi_m, __shfl_xor_sync(0xffffffffu, hi_m, d));
         lo_h = min(lo_h, __shfl_xor_sync(0xffffffffu, lo_h, d)); hi_h = max(hi_h, __shfl_xor_sync(0xffffffffu, hi_h, d));
+        hi_r = max(hi_r, __shfl_xor_sync(0xffffffffu, hi_r, d));
     }
-    if ((threadIdx.x & 31) == 0) { atomicMin(out, lo_m); atomicMax(out + 1, hi_m); atomicMin(out + 2, lo_h); atomicMax(out + 3, hi_h); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out, lo_m); atomicMax(out + 1, hi_m); atomicMin(out + 2, lo_h); atomicMax(out + 3, hi_h); atomicMax(out + 4, hi_r); }
 }
 
 template <class R>
@@ -1081,22 +1084,39 @@ pst_status pst_uniform_refresh(pst_ctx* ctx) {
     PstArray* m = pst_find(ctx, "m");
     if (n == 0 || !m) { ctx->uni_dirty = false; return PST_OK; }
     if (!ctx->d_uni) {
-        PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_uni, 4 * sizeof(unsigned long long)));
-        PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_uni, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+        PST_CUDA(ctx, cudaMalloc((void**)&ctx->d_uni, 8 * sizeof(unsigned long long)));
+        PST_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_uni, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     }
-    ctx->h_uni[0] = ctx->h_uni[2] = ~0ull; ctx->h_uni[1] = ctx->h_uni[3] = 0ull;
-    PST_CUDA(ctx, cudaMemcpyAsync(ctx->d_uni, ctx->h_uni, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_uni[0] = ctx->h_uni[2] = ~0ull; ctx->h_uni[1] = ctx->h_uni[3] = ctx->h_uni[4] = 0ull;
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->d_uni, ctx->h_uni, 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
     const unsigned grid = std::min(blocks_for(n, 256), 1184u);
-    if (ctx->f64) PST_LAUNCH(ctx, k_uniform_check<double>, grid, 256, 0, n, pst_ptr<double>(ctx, "m"), pst_ptr<double>(ctx, "h"), ctx->d_uni);
-    else PST_LAUNCH(ctx, k_uniform_check<float>, grid, 256, 0, n, pst_ptr<float>(ctx, "m"), pst_ptr<float>(ctx, "h"), ctx->d_uni);
-    PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_uni, ctx->d_uni, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->f64) PST_LAUNCH(ctx, k_uniform_check<double>, grid, 256, 0, n, pst_ptr<double>(ctx, "m"), pst_ptr<double>(ctx, "h"), pst_ptr<double>(ctx, "rad"), ctx->d_uni);
+    else PST_LAUNCH(ctx, k_uniform_check<float>, grid, 256, 0, n, pst_ptr<float>(ctx, "m"), pst_ptr<float>(ctx, "h"), pst_ptr<float>(ctx, "rad"), ctx->d_uni);
+    PST_CUDA(ctx, cudaMemcpyAsync(ctx->h_uni, ctx->d_uni, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // once per change of m / h, not per step
     auto as_double = [](unsigned long long k) { double d; std::memcpy(&d, &k, sizeof d); return d; };
     ctx->m_uniform = ctx->h_uni[0] == ctx->h_uni[1];
     ctx->m_value = as_double(ctx->h_uni[0]);
     ctx->h_uniform = pst_find(ctx, "h") && ctx->h_uni[2] == ctx->h_uni[3];
     ctx->h_value = as_double(ctx->h_uni[2]);
+    ctx->h_max = pst_find(ctx, "h") ? as_double(ctx->h_uni[3]) : 0.0;
+    ctx->rad_max = pst_find(ctx, "rad") ? as_double(ctx->h_uni[4]) : 0.0;
     ctx->uni_dirty = false;
+    return PST_OK;
+}
+
+// The stencil walkers visit one cell around a particle's own: a cutoff (kfac h, or R_i + R_j <= 2 max R for contacts) larger than
+// the cell edge would silently lose neighbours.  The largest h and radius of the owned particles are part of the device-side
+// check of uploaded data (pst_uniform_refresh: once per change of m / h / rad, no host scan), so the precondition is an error here.
+pst_status pst_check_cell_size(pst_ctx* ctx) {
+    PST_TRY(pst_uniform_refresh(ctx));
+    const double cell = ctx->grid.cell * (1.0 + 1e-12);
+    if ((ctx->cfg.physics & PST_PHYS_WCSPH) && pst_param(ctx, "kfac", 2.0) * ctx->h_max > cell)
+        return pst_fail(ctx, PST_EINVAL, "cell_size %.17g is smaller than the largest cutoff kfac * max(h) = %.17g: neighbours would be lost",
+                        ctx->grid.cell, pst_param(ctx, "kfac", 2.0) * ctx->h_max);
+    if ((ctx->cfg.physics & PST_PHYS_DEM) && 2.0 * ctx->rad_max > cell)
+        return pst_fail(ctx, PST_EINVAL, "cell_size %.17g is smaller than the largest contact distance 2 * max(rad) = %.17g: contacts would be lost",
+                        ctx->grid.cell, 2.0 * ctx->rad_max);
     return PST_OK;
 }
 
@@ -1108,6 +1128,7 @@ pst_status pst_wcsph_eos(pst_ctx* ctx) {
 
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum) {
     if (ctx->n == 0) return PST_OK;
+    PST_TRY(pst_check_cell_size(ctx));
     PST_TRY(PST_DISPATCH(ctx, launch_forces, ctx, continuity, momentum));
     ctx->pair_kernel_fn = ctx->last_kernel_fn;
     return PST_OK;

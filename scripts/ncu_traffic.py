@@ -24,11 +24,18 @@ def raw(rep):
         d = {}
         for i, k in enumerate(h):
             v = r[i]
-            if k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+            if k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum") and units[i] in scale:
                 v = float(v.replace(",", "")) * scale[units[i]]          # bytes / milliseconds
             d[k] = v
         out.append(d)
     return out
+
+
+def _f(v):
+    try:
+        return float(str(v).replace(",", ""))
+    except Exception:
+        return None
 
 
 def main():
@@ -43,6 +50,10 @@ def main():
             e = {"kernel_mangled": r["Kernel Name"], "workload": workload, "real": real,
                  "dram_bytes_per_launch": int(r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"]),
                  "kernel_ms_under_ncu": r.get("gpu__time_duration.sum"),
+                 "l1_data_pipe_pct_of_peak": _f(r.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")),
+                 "fp64_pipe_pct_of_peak": _f(r.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")),
+                 "dram_pct_of_peak": _f(r.get("dram__throughput.avg.pct_of_peak_sustained_elapsed")),
+                 "l1_hit_rate_pct": _f(r.get("l1tex__t_sector_hit_rate.pct")), "l2_hit_rate_pct": _f(r.get("lts__t_sector_hit_rate.pct")),
                  "source": "ncu --set full --clock-control none, " + os.path.basename(rep)}
             entries = [x for x in entries if not (x["kernel_mangled"] == e["kernel_mangled"] and x["workload"] == workload and x["real"] == real)]
             entries.append(e)

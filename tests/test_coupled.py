@@ -230,3 +230,21 @@ def test_coupled_300k_against_oracle():
         for k in RATES + FORCES:
             assert_close(ctx.download(k), r2[k], f"coupled 300k {k}")
         assert np.array_equal(ctx.download("hist_n"), h2["hist_n"])
+
+
+@pytest.mark.gpu
+def test_coupled_20m_against_oracle():
+    """BASELINE configs[4] at FULL size (250 x 250 x 320 lattice + floor, 20.2 M particles, 10 % spheres) on one GPU against the
+    oracle's cell-list mode with all host threads: SPH rates, contact forces and torques, stored-contact counts; plus the
+    size-independent property sum m (a - g) = 0 over fluid + spheres for the SPH part (pairwise antisymmetry)."""
+    import os
+    b = synth.coupled_block_3d(250, 250, 320)
+    orc.set_num_threads(os.cpu_count() or 1)
+    ref, hist, ov = orc.coupled(b.params, b.max_contacts, b.arrays, grid=orc.make_grid(3, b.lo, b.hi, b.cell_size))
+    assert ov == 0
+    with _ctx(b, np.float64) as ctx:
+        ctx.build_neighbours()
+        ctx.apply(["tait_eos", "continuity", "momentum", "dem_contact"])
+        for k in RATES + FORCES:
+            assert_close(ctx.download(k), ref[k], f"coupled 20M {k}")
+        assert np.array_equal(ctx.download("hist_n"), hist["hist_n"])

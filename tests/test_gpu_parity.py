@@ -476,6 +476,30 @@ def test_wcsph_step_matches_host_integration():
             assert_close(ctx.download(k), v, f"step {k}", tol=1e-12)
 
 
+def test_cell_size_precondition_is_checked():
+    """cell_size >= kfac * max(h) (SPH) and >= 2 * max(rad) (contacts): violating uploads are an error at the force pass, not
+    silently lost neighbours; fixing the data clears it."""
+    b = synth.wcsph_block_3d(8, 8, 8)
+    with _ctx(b, np.float64) as ctx:
+        h = b.arrays["h"].copy(); h[5] *= 1.5
+        ctx.upload("h", h)
+        ctx.build_neighbours()
+        with pytest.raises(pb.PstError) as e:
+            ctx.apply(["tait_eos", "continuity", "momentum"])
+        assert e.value.status == 1 and "cell_size" in str(e.value)
+        ctx.upload("h", b.arrays["h"])
+        ctx.build_neighbours()
+        ctx.apply(["tait_eos", "continuity", "momentum"])
+    d = synth.dem_column_3d(6)
+    with _ctx(d, np.float64) as ctx:
+        r = d.arrays["rad"].copy(); r[3] *= 1.2
+        ctx.upload("rad", r)
+        ctx.build_neighbours()
+        with pytest.raises(pb.PstError) as e:
+            ctx.apply(["dem_contact"])
+        assert e.value.status == 1 and "cell_size" in str(e.value)
+
+
 @pytest.mark.parametrize("case", ["wcsph2d", "wcsph3d", "dem3d"])
 def test_step_as_cuda_graph_equals_eager_steps(case):
     """Option graph = 1: pst_step captures two consecutive steps once and replays them.  The replayed kernels are the
