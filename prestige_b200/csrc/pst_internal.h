@@ -87,6 +87,9 @@ struct pst_ctx {
     // packed neighbour-state records of the tiled pair kernel (wcsph.cu: rec_*): valid while rec_epoch == state_epoch;
     // everything that changes particle state (uploads, re-sorts, halo, stages, wall pressure ...) bumps state_epoch
     void* rec = nullptr;
+    float* posf = nullptr;           // f32 copy of the positions relative to the grid origin (3 rows; written with the records): what the
+                                     // pair kernel's tiles stage by TMA bulk copies
+    size_t posf_stride = 0, posf_g4 = 0;   // row length / element 0 offset (ghost_cap rounded up to a multiple of 4: 16-byte aligned rows)
     uint64_t state_epoch = 1, rec_epoch = 0;
     // tile list of the variant-3 pair kernel (wcsph_zrun.cuh): rebuilt when the cell table changed (build_epoch)
     void* ztiles = nullptr;

@@ -88,8 +88,19 @@ constexpr int kRecRows = 5;
 // 32-bit arithmetic: the context refuses records beyond 2^31 / 5 particles (rec_alloc)
 __host__ __device__ inline int rec_index(int j) { return j + (j & ~7) * (kRecRows - 1); }
 
+// f32 position relative to the grid origin, clamped to the box + 2 cells.  The clamp keeps the f32 error bounded by the box
+// size whatever the coordinates of particles far outside (they are binned into the edge cells); it is a contraction, so a
+// distance between clamped coordinates never exceeds the true one: the pre-filter stays conservative.
 template <class R>
-struct RecSrc { const R *x, *y, *z, *u, *v, *w, *rho, *por2, *m, *h; };
+__host__ __device__ __forceinline__ float pos_f32(R x, R lo, float cmin, float cmax) {
+    const float v = (float)(x - lo);
+    return v < cmin ? cmin : (v > cmax ? cmax : v);
+}
+template <class R>
+struct PosF { float *x, *y, *z; R lo[3]; float cmin, cmax[3]; };
+
+template <class R>
+struct RecSrc { const R *x, *y, *z, *u, *v, *w, *rho, *por2, *m, *h; PosF<R> F; };
 
 template <class R>
 __device__ __forceinline__ void rec_store(R* __restrict__ rec, const RecSrc<R>& S, int s, R rho_s, R por2_s) {
@@ -100,6 +111,11 @@ __device__ __forceinline__ void rec_store(R* __restrict__ rec, const RecSrc<R>& 
     a.x = S.v[s]; a.y = S.w ? S.w[s] : (R)0; q[16] = a;
     a.x = rho_s; a.y = por2_s; q[24] = a;
     a.x = S.m[s]; a.y = S.h[s]; q[32] = a;
+    if (S.F.x) {
+        S.F.x[s] = pos_f32<R>(S.x[s], S.F.lo[0], S.F.cmin, S.F.cmax[0]);
+        S.F.y[s] = pos_f32<R>(S.y[s], S.F.lo[1], S.F.cmin, S.F.cmax[1]);
+        if (S.F.z) S.F.z[s] = pos_f32<R>(S.z[s], S.F.lo[2], S.F.cmin, S.F.cmax[2]);
+    }
 }
 
 template <class R>
@@ -132,6 +148,7 @@ __global__ void __launch_bounds__(256) k_rec_pack(int lo, int hi, R* __restrict_
 template <class R>
 struct ForceArgs {
     const R* rec;   // packed records (variant 3 with rec_impl = 1), element 0 = particle 0
+    PosF<R> F;      // ... and the f32 positions written with them (const in the pair kernel)
     R m_uni;   // UMASS kernels: the mass every particle has
     const R *x, *y, *z, *u, *v, *w, *rho, *m, *h, *por2;
     R *au, *av, *aw, *arho;
@@ -756,7 +773,25 @@ pst_status rec_alloc(pst_ctx* ctx) {
     const size_t g8 = (ctx->ghost_cap + 7) & ~(size_t)7;
     const size_t elems = (g8 + ((ctx->capacity + ctx->ghost_cap + 7) & ~(size_t)7) + 8) * kRecRows * 2;
     if (cudaMalloc(&ctx->rec, elems * (ctx->f64 ? 8 : 4)) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "neighbour-state records (%zu bytes)", elems * (ctx->f64 ? 8 : 4));
+    // f32 positions: 3 rows, element 0 at a multiple of 4 (the tiles' TMA bulk copies need 16-byte aligned sources), 8 floats of slack
+    ctx->posf_g4 = (ctx->ghost_cap + 3) & ~(size_t)3;
+    ctx->posf_stride = (ctx->posf_g4 + ctx->capacity + ctx->ghost_cap + 8 + 3) & ~(size_t)3;
+    if (cudaMalloc((void**)&ctx->posf, 3 * ctx->posf_stride * sizeof(float)) != cudaSuccess) return pst_fail(ctx, PST_ENOMEM, "f32 position rows");
+    PST_CUDA(ctx, cudaMemsetAsync(ctx->posf, 0, 3 * ctx->posf_stride * sizeof(float), ctx->stream));
     return PST_OK;
+}
+template <class R>
+PosF<R> pos_f(pst_ctx* ctx) {
+    PosF<R> F;
+    F.x = F.y = F.z = nullptr;
+    const PstGrid& g = ctx->grid;
+    for (int a = 0; a < 3; ++a) { F.lo[a] = (R)g.lo[a]; F.cmax[a] = (float)(g.n[a] / (a == g.dim - 1 ? g.sub : 1) + 2) * (float)g.cell; }
+    F.cmin = -2.0f * (float)g.cell;
+    if (ctx->posf) {
+        F.x = ctx->posf + ctx->posf_g4; F.y = F.x + ctx->posf_stride;
+        F.z = g.dim == 3 ? F.y + ctx->posf_stride : nullptr;
+    }
+    return F;
 }
 template <class R>
 RecSrc<R> rec_src(pst_ctx* ctx) {
@@ -764,6 +799,7 @@ RecSrc<R> rec_src(pst_ctx* ctx) {
     S.x = pst_ptr<R>(ctx, "x"); S.y = pst_ptr<R>(ctx, "y"); S.z = pst_ptr<R>(ctx, "z");
     S.u = pst_ptr<R>(ctx, "u"); S.v = pst_ptr<R>(ctx, "v"); S.w = pst_ptr<R>(ctx, "w");
     S.rho = pst_ptr<R>(ctx, "rho"); S.por2 = pst_ptr<R>(ctx, "por2"); S.m = pst_ptr<R>(ctx, ctx->coupled ? "msph" : "m"); S.h = pst_ptr<R>(ctx, "h");
+    S.F = pos_f<R>(ctx);
     return S;
 }
 
@@ -778,6 +814,7 @@ ForceArgs<R> make_args(pst_ctx* ctx) {
     A.n = (int)ctx->n;
     A.m_uni = (R)ctx->m_value;
     A.rec = rec_ptr<R>(ctx);
+    A.F = pos_f<R>(ctx);
     return A;
 }
 

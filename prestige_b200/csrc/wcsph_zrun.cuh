@@ -32,6 +32,8 @@ struct ZTile {
     const int4* tiles;   // (tx, ty, f0, gf) per tile
     const int* ntiles;   // device-side count
     int* next;           // dynamic tile counter (starts at 2 x grid: the first two tiles of every CTA are static)
+    float marg;          // TMA staging (global f32 coordinates): relative margin of the pre-filter on rc^2, from the box size
+    float zslack;        // ... and the slack, in fine cells, of the z-range look-up
 };
 
 constexpr int kZPad = 64;      // readable slack behind the staged rows: lanes with a short range over-scan with the warp
@@ -112,6 +114,24 @@ __global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, in
     if (!write && lane == 0) off[wid] = nt;
 }
 
+// ---- TMA (1-D bulk copy) + mbarrier, sm_90+ PTX: the staged rows of a tile are contiguous ranges of the f32 position arrays
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // predicated 8-byte shared-memory load (no branch, no wavefront for lanes whose predicate is off): a, b keep their values when p is false
 __device__ __forceinline__ void lds_u64_if(unsigned saddr, bool p, unsigned& a, unsigned& b) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}" : "+r"(a), "+r"(b) : "r"(saddr), "r"((unsigned)p) : "memory");
@@ -146,6 +166,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
     const float inv_cf = (float)S / cellf;          // 1 / fine cell edge
     const int MAXW = T.maxw;
     uint2* const my_word = s_word + tid;
+    // TMA staging needs the f32 position rows that are written with the packed records
+    constexpr bool TMA = REC;
+    __shared__ __align__(8) uint64_t s_bar;
+    if (TMA && tid == 0) mbar_init(&s_bar, 1);
+    // coordinates of the scan: TMA: relative to the grid origin (what the f32 rows hold); else: relative to the tile origin
+    const float marg = TMA ? T.marg : 1.0f / 32768.0f;
 
     // ---- stage tile k into buffer b: every warp derives the run table itself (two look-ups per lane + a shuffle scan),
     // then copies its own runs (boundaries + candidates).  No block-wide barrier inside.
@@ -167,7 +193,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
             colq = (long long)(DIM == 3 ? cx * ncy + cy : cx) * nf;
             if (okq) { gb = A.cell_start[colq + max(f0 - S, 0)]; len = A.cell_start[colq + min(f0 + gf + S, nf)] - gb; }
         }
-        const int alen = (len + 3) & ~3;            // every run starts 16-byte aligned in the staged rows
+        // every run starts 16-byte aligned in the staged rows.  TMA: the SOURCE must be aligned too, so the run is copied from the
+        // multiple of 4 below its first particle (the head and tail slack hold neighbours of the range, never scanned)
+        const int gb4 = TMA ? gb & ~3 : gb;
+        const int alen = len > 0 ? (gb - gb4 + len + 3) & ~3 : 0;
         int incl = alen;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -178,7 +207,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
         const int M = __shfl_sync(0xffffffffu, incl, NR - 1);
         const bool dense = M > min(kZJcap, T.jcap);
         if (warp == 0) {
-            if (lane < NR) { s_gbeg[lane] = gb - voff; s_voff[lane] = voff; }      // s_gbeg: global index minus staged index of the run
+            if (lane < NR) { s_gbeg[lane] = gb4 - voff; s_voff[lane] = voff; }      // s_gbeg: global index minus staged index of the run
             if (lane == NR - 1) s_voff[NR] = M;
             // i segments: the tile's own columns, fine cells [f0, f0 + gf)
             int cnt = 0, beg = 0;
@@ -199,9 +228,29 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
             if (lane < NI) { s_ibeg[lane] = beg; s_ipre[lane] = ipre - cnt; }
             if (lane == NI - 1) s_ipre[NI] = ipre;
             if (lane == 0) { s_meta[0] = t.x; s_meta[1] = t.y; s_meta[2] = f0; s_meta[3] = dense ? -gf : gf; }
+            if (TMA) {
+                // one arrival + the byte count, then every run's rows as bulk copies straight into the staged rows
+                fence_proxy_async();                 // the rows were read through the generic proxy by the previous tile
+                if (lane == 0) mbar_expect_tx(&s_bar, dense ? 0u : (unsigned)(kRows * M * (int)sizeof(float)));
+                __syncwarp();
+                if (!dense && lane < NR && alen > 0) {
+                    tma_load_1d(s_x + voff, A.F.x + gb4, (unsigned)alen * 4u, &s_bar);
+                    tma_load_1d(s_x + kZRow + voff, A.F.y + gb4, (unsigned)alen * 4u, &s_bar);
+                    if (DIM == 3) tma_load_1d(s_x + 2 * kZRow + voff, A.F.z + gb4, (unsigned)alen * 4u, &s_bar);
+                }
+            }
         }
         bool far = false;
-        if (!dense) {
+        if (TMA) {
+            if (!dense)
+                for (int q = warp; q < NR; q += NW) {      // staged offset of every fine-cell boundary of the run
+                    const int gbq = __shfl_sync(0xffffffffu, gb4, q), vo = __shfl_sync(0xffffffffu, voff, q);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)okq, q) != 0;
+                    const long long col = __shfl_sync(0xffffffffu, colq, q);
+                    for (int tt = lane; tt < W; tt += 32)
+                        s_cs[q * WM + tt] = vo + (ok ? A.cell_start[col + min(max(f0 - S + tt, 0), nf)] - gbq : 0);
+                }
+        } else if (!dense) {
             // tile-local coordinates: origin = low corner of the tile's own cells (no global load needed)
             const R ox = g.lo[0] + (R)cx0 * cellR;
             const R oy = DIM == 3 ? g.lo[1] + (R)cy0 * cellR : g.lo[1] + (R)f0 * (cellR / (R)S);
@@ -259,6 +308,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
         const R ox = g.lo[0] + (R)cx0 * cellR;
         const R oy = DIM == 3 ? g.lo[1] + (R)cy0 * cellR : g.lo[1] + (R)f0 * (cellR / (R)S);
         const R oz = DIM == 3 ? g.lo[2] + (R)f0 * (cellR / (R)S) : (R)0;
+        // origin of the scan coordinates in cells: the grid's (TMA) or the tile's
+        const int cxo = TMA ? cx0 : 0, cyo = TMA ? (DIM == 3 ? cy0 : 0) : 0, fzo = TMA ? 0 : f0;
+        const float zslack = TMA ? T.zslack : 1e-3f;
         for (int ii0 = warp * 32; ii0 < ni; ii0 += NT) {   // a warp takes 32 consecutive particles per round (warp-uniform trip count)
             const int ii = ii0 + lane;
             const bool active = ii < ni;
@@ -281,11 +333,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                     load_i<R, DIM>(I, C, A.x[gi], A.y[gi], DIM == 3 ? A.z[gi] : (R)0, A.u[gi], A.v[gi], DIM == 3 ? A.w[gi] : (R)0, A.rho[gi],
                                    A.por2[gi], A.h[gi]);
                 }
-                xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
-                // conservative f32 pre-filter: relative margin 2^-15 on rc^2 (>> the f32 error of tile-local coordinates, see
-                // launch_zrun); the range cull below uses twice that
-                rc2f = __double2float_ru((double)(UNI ? C.u_rc2 : I.rc2) * (1.0 + 1.0 / 32768.0));
-                rc2m = rc2f * (1.0f + 1.0f / 16384.0f);
+                if (TMA) {
+                    xf = pos_f32<R>(I.x, A.F.lo[0], A.F.cmin, A.F.cmax[0]); yf = pos_f32<R>(I.y, A.F.lo[1], A.F.cmin, A.F.cmax[1]);
+                    zf = DIM == 3 ? pos_f32<R>(I.z, A.F.lo[2], A.F.cmin, A.F.cmax[2]) : 0.0f;
+                } else {
+                    xf = (float)(I.x - ox); yf = (float)(I.y - oy); zf = DIM == 3 ? (float)(I.z - oz) : 0.0f;
+                }
+                // conservative f32 pre-filter: relative margin on rc^2 (2^-15 for tile-local coordinates, from the box size for
+                // grid-relative ones: see launch_zrun); the range cull below uses twice that on top
+                rc2f = __double2float_ru((double)(UNI ? C.u_rc2 : I.rc2) * (1.0 + (double)marg));
+                rc2m = rc2f * (1.0f + 2.0f * marg);
             }
             const float fz = DIM == 3 ? zf : yf;            // coordinate along the fast axis, relative to fine cell f0
             const float2 xf2 = make_float2(xf, xf), yf2 = make_float2(yf, yf), zf2 = make_float2(zf, zf);
@@ -298,11 +355,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                 q_run = (lx + ax) * RY + (DIM == 3 ? ly + ay : 0);
                 // distance from the particle to the footprint of that column (0 for its own column)
                 float dxc = 0.0f, dyc = 0.0f;
-                if (ax == 0) dxc = fmaxf(xf - (float)lx * cellf, 0.0f);
-                if (ax == 2) dxc = fmaxf((float)(lx + 1) * cellf - xf, 0.0f);
+                if (ax == 0) dxc = fmaxf(xf - (float)(cxo + lx) * cellf, 0.0f);
+                if (ax == 2) dxc = fmaxf((float)(cxo + lx + 1) * cellf - xf, 0.0f);
                 if (DIM == 3) {
-                    if (ay == 0) dyc = fmaxf(yf - (float)ly * cellf, 0.0f);
-                    if (ay == 2) dyc = fmaxf((float)(ly + 1) * cellf - yf, 0.0f);
+                    if (ay == 0) dyc = fmaxf(yf - (float)(cyo + ly) * cellf, 0.0f);
+                    if (ay == 2) dyc = fmaxf((float)(cyo + ly + 1) * cellf - yf, 0.0f);
                 }
                 const float rem = rc2m - (dxc * dxc + dyc * dyc);
                 vs = ve = 0;
@@ -310,7 +367,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                     const float zext = sqrtf(rem) * 1.00001f;
                     // fine cells [tlo, thi] relative to boundary 0 of the staged run (= fine cell f0 - S); +-1e-3 cell of slack,
                     // then clamped like the keys themselves (particles outside the box sit in the edge cells)
-                    int flo = (int)floorf((fz - zext) * inv_cf - 1e-3f) + f0, fhi = (int)floorf((fz + zext) * inv_cf + 1e-3f) + f0;
+                    int flo = (int)floorf((fz - zext) * inv_cf - zslack) + fzo, fhi = (int)floorf((fz + zext) * inv_cf + zslack) + fzo;
                     flo = min(max(flo, 0), nf - 1); fhi = min(max(fhi, 0), nf - 1);
                     const int tlo = min(max(flo - (f0 - S), 0), W - 2), thi = min(max(fhi - (f0 - S), 0), W - 2);
                     vs = s_cs[q_run * WM + tlo];
@@ -465,7 +522,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
     if (k >= ntiles) return;
     stage_tile(k, 0);
     __syncthreads();
+    unsigned phase = 0;
     for (int n = 0; k < ntiles; ++n) {
+        if (TMA) { mbar_wait(&s_bar, phase); phase ^= 1u; }  // the rows of this tile have landed
         if (tid == 0) s_next[n & 1] = atomicAdd(T.next, 1);  // tile of iteration n + 2
         compute_tile(NBUF == 2 ? n & 1 : 0);
         if (NBUF == 1) __syncthreads();                      // single buffer: everybody is done with it before it is refilled
@@ -552,6 +611,20 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
             if (!write) PST_TRY(pst_scan_exclusive(ctx, d_off, nwarps + 1));     // off[nwarps] = number of tiles
         }
         ctx->ztiles_key = key;
+    }
+    // TMA staging works on f32 coordinates relative to the GRID origin: their error grows with the box, and so must the margin of
+    // the pre-filter.  Two stored coordinates are each within half an ulp of E = the largest clamped coordinate, so a difference is
+    // off by <= ulp(E) = 2^-23 E per axis and r^2 by <= 2 rc sqrt(3) 2^-23 E (+ 3 roundings of the f32 evaluation): relative to
+    // rc^2 that is 3.5 * 2^-23 * E / rc; the margin is 8 * 2^-23 * E / rc, never below the 2^-15 of the tile-local form
+    // (tests/test_prefilter_margin.py::test_grid_relative_coordinates).  At E / rc = 333 (the 80 M tank) it is 3.2e-4: 0.1 % more
+    // candidates reach the exact test.
+    {
+        double E = 0;
+        for (int a = 0; a < DIM; ++a) E = std::max(E, (double)(g.n[a] / (a == DIM - 1 ? S : 1) + 2) * g.cell);
+        // (the SMALLEST cutoff sets the relative error: h_value is the minimum of h over the owned particles)
+        const double rc = std::max(1e-300, pst_param(ctx, "kfac", 2.0) * (ctx->h_value > 0 ? ctx->h_value : g.cell / pst_param(ctx, "kfac", 2.0)));
+        T.marg = (float)std::max(1.0 / 32768.0, 8.0 * std::ldexp(1.0, -23) * E / rc);
+        T.zslack = (float)std::max(1e-3, (double)nf * std::ldexp(1.0, -20));
     }
     T.tiles = (const int4*)ctx->ztiles;
     T.ntiles = d_off + nwarps;

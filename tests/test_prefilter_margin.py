@@ -75,3 +75,48 @@ def test_no_false_negative_near_the_cutoff(G, fused):
     assert worst < MARGIN / 2, f"worst-case f32 error {worst:.2e} is too close to the margin {MARGIN:.2e}"
     false_pos = float(np.mean(passed & ~truth & (np.abs(r2 / rc2 - 1.0) > 2 * MARGIN)))
     assert false_pos == 0.0, "pairs farther than twice the margin outside the cutoff must not survive the filter"
+
+
+@pytest.mark.parametrize("ratio", [20, 333, 5000, 200000])
+@pytest.mark.parametrize("fused", [False, True])
+def test_grid_relative_coordinates(ratio, fused):
+    """Variant 3 with TMA staging (wcsph_zrun.cuh) runs the pre-filter on f32 coordinates relative to the GRID origin, clamped to
+    the box + 2 cells, with a margin that grows with the box: max(2^-15, 8 * 2^-23 * E / rc), E = the largest clamped
+    coordinate.  Same property: never a false negative, for boxes from 20 to 200 000 cutoffs across."""
+    src = open(os.path.join(ROOT, "prestige_b200", "csrc", "wcsph_zrun.cuh")).read()
+    assert "8.0 * std::ldexp(1.0, -23) * E / rc" in src and "1.0 / 32768.0" in src
+    rng = np.random.default_rng(77 + ratio + fused)
+    n = 1_000_000
+    rc = 0.012
+    rc2 = rc * rc
+    E = ratio * rc
+    margin = max(1.0 / 32768.0, 8.0 * 2.0 ** -23 * E / rc)
+    lo = rng.uniform(-3.0, 3.0, 3)
+    xi = lo + rng.uniform(0.0, E, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    eps = 10.0 ** rng.uniform(-14, -4, n) * rng.choice([-1.0, 1.0], n)
+    xj = xi - d * (rc * (1.0 - eps))[:, None]
+    keep = np.all((xj - lo >= 0) & (xj - lo <= E), axis=1)
+    xi, xj = xi[keep], xj[keep]
+    dd = xi - xj
+    r2 = dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]
+    r2 = r2 + dd[:, 2] * dd[:, 2]
+    truth = (r2 < rc2) & (r2 > 0)
+    gi = (xi - lo).astype(np.float32)                # pos_f32: (float)(x - lo), within the clamp window here
+    gj = (xj - lo).astype(np.float32)
+    rc2f = _round_up_f32(rc2 * (1.0 + margin))
+    df = (gi - gj).astype(np.float32)
+    if fused:       # the kernel: d = fma(dz, dz, fma(dy, dy, fma(dx, dx, -rc2f))), sign bit decides
+        acc = (df[:, 0].astype(np.float64) * df[:, 0].astype(np.float64) - np.float64(rc2f)).astype(np.float32)
+        acc = (df[:, 1].astype(np.float64) * df[:, 1].astype(np.float64) + acc.astype(np.float64)).astype(np.float32)
+        acc = (df[:, 2].astype(np.float64) * df[:, 2].astype(np.float64) + acc.astype(np.float64)).astype(np.float32)
+        passed = np.signbit(acc)
+    else:
+        r2f = (df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]).astype(np.float32)
+        r2f = (r2f + df[:, 2] * df[:, 2]).astype(np.float32)
+        passed = r2f < rc2f
+    assert truth.sum() > 100000
+    assert not np.any(truth & ~passed), f"{int(np.sum(truth & ~passed))} true neighbours rejected at E / rc = {ratio}"
+    # the margin is not wasteful either: nothing farther than (1 + 3 margin) rc^2 passes
+    assert not np.any(passed & (r2 > rc2 * (1.0 + 3.0 * margin)))
