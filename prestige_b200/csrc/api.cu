@@ -376,6 +376,7 @@ pst_status pst_set_option(pst_ctx* ctx, const char* name, int value) {
         {"zsub", 1, 8},                  // fast-axis subdivision of the cell grid: 1, 2, 4 or 8
         {"tile_words", 4, 64},
         {"rec_impl", 0, 1},
+        {"fuse_eos", 0, 1},              // 1 (default): single-GPU WCSPH contexts evaluate the EOS and write the packed records inside the state permute
         {"tile_dbg", 0, 9},
         {"tile_gf", 0, 256},
         {"tile_jc", 0, 1},              // timing ablations of the variant-3 kernel (WRONG results): 1 no gathers, 2 no pair body, 3 scan only

@@ -449,10 +449,17 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
         PermuteList L;
         L.n8 = L.n4 = 0;
         std::vector<PstArray*> moved;
+        const bool fused = pst_wcsph_fused_permute(ctx);      // x y z u v w rho m h travel through k_permute_eos (wcsph.cu) instead
+        auto in_fused = [&](const PstArray& a) {
+            if (!fused || a.rows != 1) return false;
+            for (const char* nm : {"x", "y", "z", "u", "v", "w", "rho", "m", "h"}) if (a.name == nm) return true;
+            return false;
+        };
         for (int pass = 0; pass < 2; ++pass)
             for (auto& a : ctx->arrays) {
                 if (!(a.flags & PST_ARRAY_PERSISTENT) || is_history(a)) continue;
                 if ((pass == 0) != (a.esize == 8)) continue;
+                if (in_fused(a)) { if (pass == 0 || a.esize != 8) moved.push_back(&a); continue; }
                 for (int r = 0; r < a.rows; ++r) {
                     const int k = L.n8 + L.n4;
                     if (k >= kMaxPermute) return pst_fail(ctx, PST_EINVAL, "too many persistent arrays (max %d)", kMaxPermute);
@@ -462,7 +469,8 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
                 }
                 moved.push_back(&a);
             }
-        PST_LAUNCH(ctx, k_permute, blocks_for(n), kThreads, 0, L, n, ctx->vals_out);
+        if (L.n8 + L.n4 > 0) PST_LAUNCH(ctx, k_permute, blocks_for(n), kThreads, 0, L, n, ctx->vals_out);
+        if (fused) PST_TRY(pst_wcsph_permute_eos(ctx, ctx->vals_out, n));
         for (PstArray* a : moved) a->cur = 1 - a->cur;
         // Contact history: the remap is DEFERRED -- the next contact pass reads each row through vals_out (new -> old
         // index) and writes it back in place of a separate 2 x (28 Z + 4) B/particle copy.  Anything else that needs the
@@ -471,9 +479,10 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     }
     ctx->ordered = true;
     ctx->nbrs_valid = true;
-    ctx->eos_valid = false;
     ctx->state_epoch++;
     ctx->build_epoch++;
+    ctx->eos_valid = n > 0 && pst_wcsph_fused_permute(ctx);      // the fused permute has evaluated the EOS and written the records
+    if (ctx->eos_valid) ctx->rec_epoch = ctx->state_epoch;
     return PST_OK;
 }
 

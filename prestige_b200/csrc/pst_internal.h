@@ -192,6 +192,8 @@ pst_status pst_wcsph_wall_pressure(pst_ctx* ctx);                         // dum
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum);
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu
+bool pst_wcsph_fused_permute(pst_ctx* ctx);                                // wcsph.cu: the WCSPH state goes through the fused permute + EOS + records kernel
+pst_status pst_wcsph_permute_eos(pst_ctx* ctx, const uint32_t* perm, int n);
 pst_status pst_check_cell_size(pst_ctx* ctx);                             // wcsph.cu: cell_size >= kfac max(h), >= 2 max(rad)
 pst_status pst_dem_integrate(pst_ctx* ctx, double dt);
 pst_status pst_coupled_integrate(pst_ctx* ctx, double dt);                // wcsph.cu

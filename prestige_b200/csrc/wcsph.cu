@@ -103,19 +103,58 @@ template <class R>
 struct RecSrc { const R *x, *y, *z, *u, *v, *w, *rho, *por2, *m, *h; PosF<R> F; };
 
 template <class R>
-__device__ __forceinline__ void rec_store(R* __restrict__ rec, const RecSrc<R>& S, int s, R rho_s, R por2_s) {
+__device__ __forceinline__ void rec_store_vals(R* __restrict__ rec, const PosF<R>& F, int s, R x, R y, R z, R u, R v, R w, R rho_s, R por2_s, R m, R h) {
     using P = typename RecPair<R>::type;
     P* q = reinterpret_cast<P*>(rec) + rec_index(s);
-    P a; a.x = S.x[s]; a.y = S.y[s]; q[0] = a;
-    a.x = S.z ? S.z[s] : (R)0; a.y = S.u[s]; q[8] = a;
-    a.x = S.v[s]; a.y = S.w ? S.w[s] : (R)0; q[16] = a;
+    P a; a.x = x; a.y = y; q[0] = a;
+    a.x = z; a.y = u; q[8] = a;
+    a.x = v; a.y = w; q[16] = a;
     a.x = rho_s; a.y = por2_s; q[24] = a;
-    a.x = S.m[s]; a.y = S.h[s]; q[32] = a;
-    if (S.F.x) {
-        S.F.x[s] = pos_f32<R>(S.x[s], S.F.lo[0], S.F.cmin, S.F.cmax[0]);
-        S.F.y[s] = pos_f32<R>(S.y[s], S.F.lo[1], S.F.cmin, S.F.cmax[1]);
-        if (S.F.z) S.F.z[s] = pos_f32<R>(S.z[s], S.F.lo[2], S.F.cmin, S.F.cmax[2]);
+    a.x = m; a.y = h; q[32] = a;
+    if (F.x) {
+        F.x[s] = pos_f32<R>(x, F.lo[0], F.cmin, F.cmax[0]);
+        F.y[s] = pos_f32<R>(y, F.lo[1], F.cmin, F.cmax[1]);
+        if (F.z) F.z[s] = pos_f32<R>(z, F.lo[2], F.cmin, F.cmax[2]);
     }
+}
+template <class R>
+__device__ __forceinline__ void rec_store(R* __restrict__ rec, const RecSrc<R>& S, int s, R rho_s, R por2_s) {
+    rec_store_vals<R>(rec, S.F, s, S.x[s], S.y[s], S.z ? S.z[s] : (R)0, S.u[s], S.v[s], S.w ? S.w[s] : (R)0, rho_s, por2_s, S.m[s], S.h[s]);
+}
+
+// Tait EOS in the cancellation-free form (same as the oracle): p = B expm1(gamma log1p(rho/rho0 - 1))
+template <class R>
+__device__ __forceinline__ R tait_pressure(const WcsphConst<R>& C, R rho) {
+    const R e = (rho - C.rho0) / C.rho0;
+    return C.B * expm1(C.gamma * log1p(e));
+}
+
+// Re-sort + EOS + records in ONE pass (single-GPU WCSPH contexts with packed records): the state permute already holds
+// x y z u v w rho m h of a particle in registers, so it also evaluates the EOS and writes p, p/rho^2, the packed record and the
+// f32 position -- instead of k_eos reading the nine arrays back (76 B per particle and step less HBM traffic, one launch less).
+template <class R>
+struct PermEosArgs {
+    const R* src[9];      // x y z u v w rho m h (z, w null in 2D), the buffers of the OLD order
+    R* dst[9];
+    R *p, *por2, *rec;
+    PosF<R> F;
+};
+template <class R>
+__global__ void __launch_bounds__(256) k_permute_eos(WcsphConst<R> C, int n, const uint32_t* __restrict__ perm, PermEosArgs<R> P) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t o = perm[s];
+    R v[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) v[a] = P.src[a] ? __ldg(P.src[a] + o) : (R)0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+        if (P.dst[a]) P.dst[a][s] = v[a];
+    const R pr = tait_pressure<R>(C, v[6]);
+    const R q = pr / (v[6] * v[6]);
+    P.p[s] = pr;
+    P.por2[s] = q;
+    rec_store_vals<R>(P.rec, P.F, s, v[0], v[1], v[2], v[3], v[4], v[5], v[6], q, v[7], v[8]);
 }
 
 template <class R>
@@ -129,9 +168,7 @@ __global__ void __launch_bounds__(256) k_eos(WcsphConst<R> C, int lo, int hi, co
         msph[s] = t == 0 ? m[s] : (t == 2 ? -(m[s] * solid_ratio) : -m[s]);
     }
     const R r = rho[s];
-    // (rho/rho0)^gamma - 1 without cancellation near rho0 (same form as the oracle)
-    const R e = (r - C.rho0) / C.rho0;
-    const R pr = C.B * expm1(C.gamma * log1p(e));
+    const R pr = tait_pressure<R>(C, r);        // (rho/rho0)^gamma - 1 without cancellation near rho0 (same form as the oracle)
     const R q = pr / (r * r);
     p[s] = pr;
     por2[s] = q;
@@ -1157,7 +1194,36 @@ pst_status pst_check_cell_size(pst_ctx* ctx) {
     return PST_OK;
 }
 
+// nnps.cu asks before it builds its permute list: does the WCSPH state travel through the fused permute + EOS kernel?
+bool pst_wcsph_fused_permute(pst_ctx* ctx) {
+    return (ctx->cfg.physics & PST_PHYS_WCSPH) && !ctx->coupled && !ctx->comm && rec_wanted(ctx) && pst_option(ctx, "fuse_eos", 1) == 1 &&
+           pst_find(ctx, "rho") && pst_find(ctx, "p") && pst_find(ctx, "por2");
+}
+
+template <class R>
+static pst_status launch_permute_eos(pst_ctx* ctx, const uint32_t* perm, int n) {
+    PST_TRY(rec_alloc(ctx));
+    PermEosArgs<R> P;
+    const char* names[9] = {"x", "y", "z", "u", "v", "w", "rho", "m", "h"};
+    for (int a = 0; a < 9; ++a) {
+        PstArray* arr = pst_find(ctx, names[a]);
+        P.src[a] = arr ? pst_ptr<R>(ctx, arr, 0, arr->cur) : nullptr;
+        P.dst[a] = arr ? pst_ptr<R>(ctx, arr, 0, 1 - arr->cur) : nullptr;
+    }
+    P.p = pst_ptr<R>(ctx, "p"); P.por2 = pst_ptr<R>(ctx, "por2");
+    P.rec = rec_ptr<R>(ctx);
+    P.F = pos_f<R>(ctx);
+    PST_LAUNCH(ctx, k_permute_eos<R>, blocks_for(n, 256), 256, 0, make_const<R>(ctx), n, perm, P);
+    return PST_OK;
+}
+// the caller (build_pass) flips the nine arrays afterwards and marks EOS and records current
+pst_status pst_wcsph_permute_eos(pst_ctx* ctx, const uint32_t* perm, int n) {
+    return ctx->f64 ? launch_permute_eos<double>(ctx, perm, n) : launch_permute_eos<float>(ctx, perm, n);
+}
+
 pst_status pst_wcsph_eos(pst_ctx* ctx) {
+    // nothing to do when the re-sort has just evaluated it (fused permute) and nothing changed since
+    if (ctx->eos_valid && ctx->rec && ctx->rec_epoch == ctx->state_epoch && pst_wcsph_fused_permute(ctx)) return PST_OK;
     PST_TRY(ctx->f64 ? launch_eos<double>(ctx) : launch_eos<float>(ctx));
     ctx->eos_valid = true;
     return PST_OK;

@@ -284,8 +284,14 @@ def test_errors_are_loud():
         with pytest.raises(pb.PstError):
             ctx.upload("nope", np.zeros(b.n))
         ctx.build_neighbours()
+        ctx.upload("rho", b.arrays["rho"] * 1.001)
         with pytest.raises(pb.PstError):
-            ctx.apply(["momentum"])              # p not computed yet
+            ctx.apply(["momentum"])              # rho changed after the re-sort (which evaluates the EOS): p is not current
+        ctx.set_option("fuse_eos", 0)
+        ctx.build_neighbours()
+        with pytest.raises(pb.PstError):
+            ctx.apply(["momentum"])              # without the fused permute: p not computed yet
+        ctx.set_option("fuse_eos", 1)
         with pytest.raises(pb.PstError):
             ctx.apply(["dem_contact"])           # wrong physics
     with pytest.raises(pb.PstError):
@@ -474,6 +480,32 @@ def test_wcsph_step_matches_host_integration():
         ctx.step(dt, 1)
         for k, v in exp.items():
             assert_close(ctx.download(k), v, f"step {k}", tol=1e-12)
+
+
+@pytest.mark.parametrize("real", REALS)
+@pytest.mark.parametrize("dim", [3, 2])
+def test_fused_permute_eos_equals_separate_passes(real, dim):
+    """Single-GPU WCSPH contexts evaluate the EOS and write the packed records inside the state permute (option fuse_eos,
+    default 1): p, the rates and the re-sorted state must be bit-identical to the separate passes, tait_eos afterwards is a
+    no-op, and a state change after the re-sort (an upload) brings the separate EOS pass back."""
+    b = (synth.wcsph_block_3d(14, 12, 16) if dim == 3 else synth.wcsph_dambreak_2d(dx=0.04)).shuffled().astype(real)
+    names = ["p", "au", "av", "arho", "x", "rho"] + (["aw"] if dim == 3 else [])
+    out = {}
+    for fuse in (1, 0):
+        with _ctx(b, real) as ctx:
+            ctx.set_option("fuse_eos", fuse)
+            ctx.build_neighbours()
+            l0 = ctx.stat("launches")
+            ctx.apply(["tait_eos"])
+            assert (ctx.stat("launches") == l0) == bool(fuse)       # fused: nothing left to do
+            ctx.apply(["continuity", "momentum"])
+            out[fuse] = {k: ctx.download(k) for k in names}
+            rho2 = b.arrays["rho"] * real(1.002)
+            ctx.upload("rho", rho2)
+            ctx.apply(["tait_eos", "continuity", "momentum"])
+            out[fuse]["p2"] = ctx.download("p")
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k]), f"{k}: fused permute + EOS differs from the separate passes"
 
 
 def test_cell_size_precondition_is_checked():

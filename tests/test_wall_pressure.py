@@ -198,6 +198,7 @@ def test_wall_pressure_step_and_errors():
         with pytest.raises(pb.PstError):
             ctx.apply(["wall_pressure"])                    # no neighbours yet
         ctx.build_neighbours()
+        ctx.upload("rho", b.arrays["rho"])                  # (the re-sort of a single-GPU context evaluates the EOS: touch rho)
         with pytest.raises(pb.PstError):
             ctx.apply(["wall_pressure"])                    # p of the fluid is not current
         ctx.apply(["tait_eos"])
