@@ -554,12 +554,12 @@ pst_status pst_apply(pst_ctx* ctx, const char* const* eq_names, int n_eq) {
     if (eqs.count("tait_eos")) PST_TRY(pst_wcsph_eos(ctx));
     if (eqs.count("wall_pressure")) {   // per dummy particle, a gather over its fluid neighbours: after the EOS, before the pair kernel reads p[j]
         if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before wall_pressure");
-        if (!ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "wall_pressure reads p of the fluid: apply tait_eos first (or in the same set)");
+        if (!ctx->eos_valid || ctx->ghost_eos_pending) return pst_fail(ctx, PST_ESTATE, "wall_pressure reads p of the fluid: apply tait_eos first (or in the same set)");
         PST_TRY(pst_wcsph_wall_pressure(ctx));
     }
     if (eqs.count("continuity") || eqs.count("momentum")) {
         if (!ctx->nbrs_valid) return pst_fail(ctx, PST_ESTATE, "pst_build_neighbours must run before pair equations");
-        if ((eqs.count("momentum") || ctx->coupled) && !ctx->eos_valid) return pst_fail(ctx, PST_ESTATE, "momentum reads p: apply tait_eos first (or in the same set)");
+        if ((eqs.count("momentum") || ctx->coupled) && (!ctx->eos_valid || ctx->ghost_eos_pending)) return pst_fail(ctx, PST_ESTATE, "momentum reads p: apply tait_eos first (or in the same set)");
         if (ctx->coupled && !(eqs.count("continuity") && eqs.count("momentum")))
             return pst_fail(ctx, PST_EINVAL, "coupled contexts fuse continuity and momentum: apply both in one set");
         PST_TRY(pst_wcsph_forces(ctx, eqs.count("continuity") > 0, eqs.count("momentum") > 0));

@@ -403,7 +403,7 @@ pst_status pst_migrate(pst_ctx* ctx, int* arrivals) {
             }
     }
     ctx->n = (uint64_t)(n_stay + aL + aR);
-    ctx->state_epoch++;
+    if (aL + aR > 0) ctx->state_epoch++;      // (leavers alone only shorten the owned range: the rows that stay, and their records, are untouched)
     if (aL + aR > 0) ctx->uni_dirty = true;   // arrivals carry their own m and h
     *arrivals = aL + aR;
     return PST_OK;
@@ -539,7 +539,7 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
             ctx->n_ghost_l = left >= 0 ? W : 0;
             ctx->n_ghost_r = right >= 0 ? W : 0;
             ctx->ghost_exact = false;
-            ctx->eos_valid = false; ctx->state_epoch++;
+            pst_note_ghosts_changed(ctx);
             return PST_OK;
             }      // (no peer access on this machine: fall through to the packed NCCL message)
         }
@@ -571,7 +571,7 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
         ctx->n_ghost_l = left >= 0 ? W : 0;
         ctx->n_ghost_r = right >= 0 ? W : 0;
         ctx->ghost_exact = false;
-        ctx->eos_valid = false; ctx->state_epoch++;
+        pst_note_ghosts_changed(ctx);
         return PST_OK;
     }
     // 1. where do my edge layers start and end?  (4 table entries -> host)
@@ -637,6 +637,6 @@ extern "C" pst_status pst_halo_exchange(pst_ctx* ctx) {
     ctx->n_ghost_l = nL;
     ctx->n_ghost_r = nR;
     ctx->ghost_exact = true;
-    ctx->eos_valid = false; ctx->state_epoch++;
+    pst_note_ghosts_changed(ctx);
     return PST_OK;
 }

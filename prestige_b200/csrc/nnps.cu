@@ -481,6 +481,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
     ctx->nbrs_valid = true;
     ctx->state_epoch++;
     ctx->build_epoch++;
+    ctx->ghost_eos_pending = false;                              // (no ghost rows until the next halo exchange)
     ctx->eos_valid = n > 0 && pst_wcsph_fused_permute(ctx);      // the fused permute has evaluated the EOS and written the records
     if (ctx->eos_valid) ctx->rec_epoch = ctx->state_epoch;
     return PST_OK;

@@ -91,6 +91,7 @@ struct pst_ctx {
                                      // pair kernel's tiles stage by TMA bulk copies
     size_t posf_stride = 0, posf_g4 = 0;   // row length / element 0 offset (ghost_cap rounded up to a multiple of 4: 16-byte aligned rows)
     uint64_t state_epoch = 1, rec_epoch = 0;
+    bool ghost_eos_pending = false;  // the owned rows' EOS and records are current (fused permute), the ghost rows just arrived: tait_eos runs over them alone
     // tile list of the variant-3 pair kernel (wcsph_zrun.cuh): rebuilt when the cell table changed (build_epoch)
     void* ztiles = nullptr;
     size_t ztiles_cap = 0, ztile_off_cap = 0;
@@ -192,6 +193,7 @@ pst_status pst_wcsph_wall_pressure(pst_ctx* ctx);                         // dum
 pst_status pst_wcsph_forces(pst_ctx* ctx, bool continuity, bool momentum);
 pst_status pst_wcsph_integrate(pst_ctx* ctx, double dt);
 pst_status pst_dem_forces(pst_ctx* ctx);                                  // dem.cu
+void pst_note_ghosts_changed(pst_ctx* ctx);                                // wcsph.cu: a halo exchange wrote the ghost rows
 bool pst_wcsph_fused_permute(pst_ctx* ctx);                                // wcsph.cu: the WCSPH state goes through the fused permute + EOS + records kernel
 pst_status pst_wcsph_permute_eos(pst_ctx* ctx, const uint32_t* perm, int n);
 pst_status pst_check_cell_size(pst_ctx* ctx);                             // wcsph.cu: cell_size >= kfac max(h), >= 2 max(rad)

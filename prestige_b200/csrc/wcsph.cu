@@ -938,7 +938,14 @@ pst_status launch_tiled(pst_ctx* ctx, bool cont, bool mom) {
 // bring the packed records up to date (no-op when the EOS pass has just written them)
 template <class R>
 pst_status rec_refresh(pst_ctx* ctx) {
-    if (ctx->rec && ctx->rec_epoch == ctx->state_epoch) return PST_OK;
+    if (ctx->rec && ctx->rec_epoch == ctx->state_epoch) {
+        if (ctx->ghost_eos_pending) {       // ghost rows arrived after the fused permute and no EOS pass has run over them yet (continuity alone)
+            const int n = (int)ctx->n, nl = (int)ctx->n_ghost_l, nr = (int)ctx->n_ghost_r;
+            if (nl > 0) PST_LAUNCH(ctx, k_rec_pack<R>, blocks_for(nl, 256), 256, 0, -nl, 0, rec_ptr<R>(ctx), rec_src<R>(ctx));
+            if (nr > 0) PST_LAUNCH(ctx, k_rec_pack<R>, blocks_for(nr, 256), 256, 0, n, n + nr, rec_ptr<R>(ctx), rec_src<R>(ctx));
+        }
+        return PST_OK;
+    }
     PST_TRY(rec_alloc(ctx));
     const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r;
     if (hi > lo) PST_LAUNCH(ctx, k_rec_pack<R>, blocks_for(hi - lo, 256), 256, 0, lo, hi, rec_ptr<R>(ctx), rec_src<R>(ctx));
@@ -1052,8 +1059,7 @@ pst_status launch_coupled_integrate(pst_ctx* ctx, double dt) {
 }
 
 template <class R>
-pst_status launch_eos(pst_ctx* ctx) {
-    const int lo = -(int)ctx->n_ghost_l, hi = (int)ctx->n + (int)ctx->n_ghost_r;
+pst_status launch_eos(pst_ctx* ctx, int lo, int hi) {
     if (hi <= lo) return PST_OK;
     const double rs = pst_param(ctx, "rho_solid", 0.0);
     if (ctx->coupled && !(rs > 0)) return pst_fail(ctx, PST_EINVAL, "coupled context: parameter rho_solid must be > 0");
@@ -1196,7 +1202,7 @@ pst_status pst_check_cell_size(pst_ctx* ctx) {
 
 // nnps.cu asks before it builds its permute list: does the WCSPH state travel through the fused permute + EOS kernel?
 bool pst_wcsph_fused_permute(pst_ctx* ctx) {
-    return (ctx->cfg.physics & PST_PHYS_WCSPH) && !ctx->coupled && !ctx->comm && rec_wanted(ctx) && pst_option(ctx, "fuse_eos", 1) == 1 &&
+    return (ctx->cfg.physics & PST_PHYS_WCSPH) && !ctx->coupled && rec_wanted(ctx) && pst_option(ctx, "fuse_eos", 1) == 1 &&
            pst_find(ctx, "rho") && pst_find(ctx, "p") && pst_find(ctx, "por2");
 }
 
@@ -1221,11 +1227,29 @@ pst_status pst_wcsph_permute_eos(pst_ctx* ctx, const uint32_t* perm, int n) {
     return ctx->f64 ? launch_permute_eos<double>(ctx, perm, n) : launch_permute_eos<float>(ctx, perm, n);
 }
 
+// A halo exchange wrote the ghost rows.  If the owned rows' EOS and records are current (the fused permute of this step), they stay
+// so: only the ghost rows are pending, and tait_eos will run over those alone (two short ranges instead of the whole slab).
+void pst_note_ghosts_changed(pst_ctx* ctx) {
+    const bool keep = ctx->eos_valid && ctx->rec && ctx->rec_epoch == ctx->state_epoch && pst_wcsph_fused_permute(ctx);
+    ctx->state_epoch++;
+    if (keep) { ctx->rec_epoch = ctx->state_epoch; ctx->ghost_eos_pending = true; }
+    else ctx->eos_valid = false;
+}
+
 pst_status pst_wcsph_eos(pst_ctx* ctx) {
-    // nothing to do when the re-sort has just evaluated it (fused permute) and nothing changed since
-    if (ctx->eos_valid && ctx->rec && ctx->rec_epoch == ctx->state_epoch && pst_wcsph_fused_permute(ctx)) return PST_OK;
-    PST_TRY(ctx->f64 ? launch_eos<double>(ctx) : launch_eos<float>(ctx));
+    const int n = (int)ctx->n, nl = (int)ctx->n_ghost_l, nr = (int)ctx->n_ghost_r;
+    // nothing to do for the owned rows when the re-sort has just evaluated them (fused permute) and nothing changed since
+    if (ctx->eos_valid && ctx->rec && ctx->rec_epoch == ctx->state_epoch && pst_wcsph_fused_permute(ctx)) {
+        if (ctx->ghost_eos_pending) {
+            PST_TRY(ctx->f64 ? launch_eos<double>(ctx, -nl, 0) : launch_eos<float>(ctx, -nl, 0));
+            PST_TRY(ctx->f64 ? launch_eos<double>(ctx, n, n + nr) : launch_eos<float>(ctx, n, n + nr));
+            ctx->ghost_eos_pending = false;
+        }
+        return PST_OK;
+    }
+    PST_TRY(ctx->f64 ? launch_eos<double>(ctx, -nl, n + nr) : launch_eos<float>(ctx, -nl, n + nr));
     ctx->eos_valid = true;
+    ctx->ghost_eos_pending = false;
     return PST_OK;
 }
 
