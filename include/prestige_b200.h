@@ -135,7 +135,8 @@ PST_API void pst_host_free(void* p);
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* cell keys -> radix sort -> cell start table -> permute persistent state (+ history remap) */
 PST_API pst_status pst_build_neighbours(pst_ctx* ctx);
-/* fuse(): run the hand-written fused kernel for this equation set, bodies in the given order.
+/* fuse(): run the hand-written fused kernels for this equation SET (order and duplicates in eq_names do not matter: the
+ * library runs tait_eos, wall_pressure, the fused continuity / momentum pair kernel, dem_contact, body_reduce in that order).
  * Known names: "eq1" | "tait_eos" "wall_pressure" "continuity" "momentum" | "dem_contact" | "body_reduce"
  * "wall_pressure" (no reference code): every non-fluid particle (tag != 0) takes the pressure
  * extrapolated from its fluid neighbours, p_w = sum (p_f + rho_f g . x_wf) W_wf / sum W_wf, and the density the EOS

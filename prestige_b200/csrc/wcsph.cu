@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(kThreads) k_wall_pressure(GridDev<R> g, WcsphC
                                                             const int32_t* __restrict__ idx, const int32_t* __restrict__ tag,
                                                             const R* __restrict__ x, const R* __restrict__ y, const R* __restrict__ z,
                                                             const R* __restrict__ h, R* rho, R* p, R* __restrict__ por2,
-                                                            const int32_t* __restrict__ cell_start) {
+                                                            const int32_t* __restrict__ cell_start, PosF<R> F, float marg) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= pos[n]) return;                 // pos[n] = number of non-fluid particles (device-side count, no host sync)
     const int s = idx[t];
@@ -1114,11 +1114,33 @@ __global__ void __launch_bounds__(kThreads) k_wall_pressure(GridDev<R> g, WcsphC
     const int cy = cell_coord<R>(yi, g.lo[1], g.inv[1], 0, g.n[1] - 1);
     const int cz = DIM == 3 ? cell_coord<R>(zi, g.lo[2], g.inv[2], 0, g.n[2] - 1) : 0;
     WallSums<R> S{0, 0, 0, 0, 0};
+    // With the f32 position rows of the packed records at hand (F.x != null) the ~370 candidates are pre-filtered in f32 -- the
+    // pair kernel's conservative test, same margin -- and only the survivors (~58) reach the f64 loads and the exact test.
+    const bool pre = F.x != nullptr;
+    const float xf = pre ? pos_f32<R>(xi, F.lo[0], F.cmin, F.cmax[0]) : 0.0f, yf = pre ? pos_f32<R>(yi, F.lo[1], F.cmin, F.cmax[1]) : 0.0f;
+    const float zf = pre && DIM == 3 ? pos_f32<R>(zi, F.lo[2], F.cmin, F.cmax[2]) : 0.0f;
+    const float rc2f = pre ? __double2float_ru((double)rc2 * (1.0 + (double)marg)) : 0.0f;
+    auto exact = [&](int j) {
+        const R dx = xi - x[j], dy = yi - y[j], dz = DIM == 3 ? zi - z[j] : (R)0;
+        const R r2 = dist2<DIM, R>(dx, dy, dz);
+        if (r2 < rc2 && r2 > (R)0 && tag[j] == 0) wall_accumulate<R, DIM>(S, ad, inv_h, dx, dy, dz, r2, p[j], rho[j]);
+    };
     for_each_run<DIM, MORTON>(g, cell_start, cx, cy, cz, [&](int b, int e) {
-        for (int j = b; j < e; ++j) {
-            const R dx = xi - x[j], dy = yi - y[j], dz = DIM == 3 ? zi - z[j] : (R)0;
-            const R r2 = dist2<DIM, R>(dx, dy, dz);
-            if (r2 < rc2 && r2 > (R)0 && tag[j] == 0) wall_accumulate<R, DIM>(S, ad, inv_h, dx, dy, dz, r2, p[j], rho[j]);
+        if (!pre) {
+            for (int j = b; j < e; ++j) exact(j);
+            return;
+        }
+        for (int j0 = b; j0 < e; j0 += 8) {       // eight candidates' loads in flight per trip (the loop is latency-bound)
+            float d[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int j = min(j0 + t, e - 1);
+                const float ex = xf - F.x[j], ey = yf - F.y[j], ez = DIM == 3 ? zf - F.z[j] : 0.0f;
+                d[t] = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (j0 + t < e && d[t] <= rc2f) exact(j0 + t);
         }
     });
     R pv, rw;
@@ -1141,10 +1163,24 @@ pst_status launch_wall_pressure(pst_ctx* ctx) {
     PST_LAUNCH(ctx, k_wp_flags, blocks_for(n + 1, 256), 256, 0, n, tag, ctx->wp_pos);
     PST_TRY(pst_scan_exclusive(ctx, ctx->wp_pos, n + 1));
     PST_LAUNCH(ctx, k_wp_fill, blocks_for(n, 256), 256, 0, n, tag, ctx->wp_pos, ctx->wp_idx);
+    // f32 pre-filter: only when the f32 position rows are current (written with the packed records by the EOS pass that must
+    // precede this equation) and the keys are linear; the margin is the pair kernel's (wcsph_zrun.cuh: 8 * 2^-23 * E / rc)
+    PosF<R> F = pos_f<R>(ctx);
+    PST_TRY(pst_uniform_refresh(ctx));
+    if (MORTON || !ctx->rec || ctx->rec_epoch != ctx->state_epoch || ctx->ghost_eos_pending) F.x = F.y = F.z = nullptr;
+    float marg = 0.0f;
+    {
+        const PstGrid& gg = ctx->grid;
+        double E = 0;
+        for (int a = 0; a < DIM; ++a) E = std::max(E, (double)(gg.n[a] / (a == DIM - 1 ? gg.sub : 1) + 2) * gg.cell);
+        const double kf = pst_param(ctx, "kfac", 2.0);
+        const double rc = std::max(1e-300, kf * (ctx->h_value > 0 ? ctx->h_value : gg.cell / kf));
+        marg = (float)std::max(1.0 / 32768.0, 8.0 * std::ldexp(1.0, -23) * E / rc);
+    }
     // the grid covers the worst case (every particle a dummy); threads beyond the device-side count exit at once
     PST_LAUNCH(ctx, (k_wall_pressure<R, DIM, MORTON>), blocks_for(n, kThreads), kThreads, 0, make_grid_dev<R>(ctx->grid), make_const<R>(ctx), n,
                ctx->wp_pos, ctx->wp_idx, tag, pst_ptr<R>(ctx, "x"), pst_ptr<R>(ctx, "y"), pst_ptr<R>(ctx, "z"), pst_ptr<R>(ctx, "h"),
-               pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "p"), pst_ptr<R>(ctx, "por2"), ctx->cell_start);
+               pst_ptr<R>(ctx, "rho"), pst_ptr<R>(ctx, "p"), pst_ptr<R>(ctx, "por2"), ctx->cell_start, F, marg);
     return PST_OK;
 }
 
@@ -1153,8 +1189,9 @@ pst_status launch_wall_pressure(pst_ctx* ctx) {
 pst_status pst_wcsph_wall_pressure(pst_ctx* ctx) {
     if (ctx->n == 0) return PST_OK;
     if (ctx->comm) return pst_fail(ctx, PST_EINVAL, "wall_pressure is single-GPU for now: ghost dummy particles would need a second density exchange");
+    const pst_status st = PST_DISPATCH(ctx, launch_wall_pressure, ctx);   // (reads the f32 position rows while they are still current)
     ctx->state_epoch++;     // rho, p, p/rho^2 of the non-fluid rows change: packed records are stale
-    return PST_DISPATCH(ctx, launch_wall_pressure, ctx);
+    return st;
 }
 
 pst_status pst_uniform_refresh(pst_ctx* ctx) {

@@ -3,26 +3,29 @@
 // No reference code exists for the physics; the loop shape it honours is the reference's
 // gather -- write only [i], bodies of a fused set in ONE i,j loop (prestige/src/codegen/simple_cpu.rs:7-16, fuse.rs:14-40).
 //
-// What changed against variant 2 (k_wcsph_tiled), and why (profiles/r2_ncu_k_wcsph_tiled_10m_base.txt: 43 % of the warp
-// samples sat in the candidate scan, 22 % in the tile preamble, 33 % in the pair bodies; L1 data pipe 80 % busy):
+// The design in one place (DESIGN.md section 4 has the measurements; profiles/r2_exp_log.txt every step on the way):
 //   * the cell grid is `sub` times finer along the FAST axis (option zsub; nnps.cu sorts by the fine key), so inside a
 //     stencil column the particles are ordered by fine z.  A particle scans, per column, only the fine cells within
 //     +-sqrt(rc^2 - d_xy^2) of its own z, d_xy = its distance to that column's footprint: ~190 candidates instead of the
 //     373 of the 27-cell stencil;
 //   * the scan produces BIT MASKS, not lists: d = dx^2 + dy^2 + dz^2 - rc^2 comes out of three packed FFMA2, its sign bit
 //     is funnel-shifted into a 32-bit word (one SHF per candidate, no compare, no predicated store, no serial list
-//     pointer), one word per 32 scanned candidates, empty words dropped;
+//     pointer); non-empty words are kept as 8 bytes (mask, global index of the word's first candidate + 31);
 //   * all lanes of a warp scan a run in lock-step (trip count = the warp's longest range, the surplus bits are cut off),
 //     every LDS.128 is 16-byte aligned by construction (runs are staged at multiples of 4, ranges start aligned down);
-//   * staging holds 12 B per candidate (f32 tile-local x, y, z; the global index follows from the word's base);
-//   * the neighbour state of a hit comes from packed AoSoA records (wcsph.cu rec_*): 4 x LDG.128 off one address;
-//   * tiles are cut by a small kernel from the cell table so that every tile holds at most one particle per thread and
-//     nearly that many (k_ztile_list: greedy along the fast axis, empty stretches skipped);
-//   * CTAs are PERSISTENT and double-buffered: while the warps of a CTA evaluate tile n, each warp that finishes stages its
-//     share of tile n + 1 into the other buffer -- the table look-ups and the staging loads overlap the pair bodies of the
-//     other warps instead of idling the SM at the head of every CTA (one __syncthreads per tile).
-// The pair bodies (phase 2) are those of variant 2: the exact FMA-free test decides membership, so the neighbour set stays
-// bit-exact.
+//   * staging holds 12 B per candidate: f32 coordinates relative to the GRID origin, copied by TMA (cp.async.bulk +
+//     mbarrier) out of the f32 position rows that are written with the packed records; without records (rec_impl = 0) the
+//     warps convert tile-local coordinates on the fly;
+//   * phase 2 is software-pipelined and branch-free: a count-leading-zeros iterator over the words (one predicated LDS.64
+//     per refill) runs one hit ahead of the gathers, the gathers -- 4 x LDG.128 off one address into the packed AoSoA
+//     records (wcsph.cu rec_*) -- one body ahead of their use; the exact FMA-free f64 test on the gathered record decides
+//     membership, so the neighbour set stays bit-exact;
+//   * tiles are cut on the device from the cell table (k_ztile_list: 2 x 2 columns x as many fine cells as hold <= 2 NT own
+//     particles and <= 2560 staged candidates; list in (tx, ty, f0) order so neighbouring tiles meet in L2);
+//   * CTAs are PERSISTENT (2 per SM), fetch tiles from an atomic counter, and every warp evaluates two rows of 32 particles
+//     per tile; ONE staging buffer (TMA makes the refill cheap; two buffers of half the size measured slower).
+// The unit this kernel sits on is the L1 data pipe (90 % busy: the 64-byte gathers cost ~36 wavefronts per warp whatever the
+// layout), not HBM and not FP64.
 
 struct ZTile {
     int gfcap;       // deepest tile, in fine cells
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
             const bool active = ii < ni;
             int c = 0, gi = 0, lx = 0, ly = 0;
             IState<R, DIM> I;
-            Acc<R> a{0, 0, 0, 0}, a2{0, 0, 0, 0};
+            Acc<R> a{0, 0, 0, 0};
             float xf = 0, yf = 0, zf = 0, rc2f = 0, rc2m = -1.0f;
             bool fluid_i = true;
             if (active) {
@@ -506,7 +509,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
                 if (k == NRUN) break;      // warp-uniform
             }
             if (active) {
-                a.au += a2.au; a.av += a2.av; a.aw += a2.aw; a.arho += a2.arho;
                 store_acc<R, DIM, CONT, MOM>(A, C, gi, a);
             }
         }
