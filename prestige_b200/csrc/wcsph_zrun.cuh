@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_wcsph_zrun(GridDev<R> g, Wcsph
     // TMA staging needs the f32 position rows that are written with the packed records
     constexpr bool TMA = REC;
     __shared__ __align__(8) uint64_t s_bar;
-    if (TMA && tid == 0) mbar_init(&s_bar, 1);
+    if (TMA) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();          // the barrier object is initialised before anybody arrives on it or waits for it
+    }
     // coordinates of the scan: TMA: relative to the grid origin (what the f32 rows hold); else: relative to the tile origin
     const float marg = TMA ? T.marg : 1.0f / 32768.0f;
 
