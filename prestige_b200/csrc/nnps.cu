@@ -416,8 +416,10 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
         if (n > 0) PST_TRY(PST_DISPATCH(ctx, launch_keys_count, ctx, mig_l, mig_r));
         const int nb = (m + kScanTile - 1) / kScanTile;
         PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums, ctx->d_counters, ctx->grid.sub);
-        PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
-        PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums);
+        if (nb > 1) {
+            PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
+            PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, ctx->cell_start, ctx->scan_sums);
+        }
         if (n > 0) {
             PST_LAUNCH(ctx, k_place, blocks_for(n), kThreads, 0, n, ctx->keys_in, ctx->vals_in, ctx->cell_start, ctx->vals_out);
             PST_LAUNCH(ctx, k_cell_order, blocks_for(nkeys), kThreads, 0, nkeys, ctx->cell_start, ctx->vals_out, ctx->keys_out, ctx->d_counters);
@@ -508,8 +510,10 @@ pst_status pst_scan_exclusive(pst_ctx* ctx, int32_t* a, int m) {
         PST_CUDA(ctx, cudaMalloc((void**)&ctx->scan_sums, ctx->scan_sums_cap * 4));
     }
     PST_LAUNCH(ctx, k_scan_tiles, nb, kScanThreads, 0, m, a, ctx->scan_sums, (unsigned long long*)nullptr, 1);
-    PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
-    PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, a, ctx->scan_sums);
+    if (nb > 1) {       // (one tile: its local scan is the scan)
+        PST_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, nb, ctx->scan_sums);
+        PST_LAUNCH(ctx, k_scan_add, nb, kScanThreads, 0, m, a, ctx->scan_sums);
+    }
     return PST_OK;
 }
 
