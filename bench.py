@@ -347,8 +347,12 @@ def traffic_for(kernel_mangled: str, workload: str, real: str):
         return None, "no profiles/traffic.json", None
     with open(tp) as f:
         t = json.load(f)
+    import re
+
+    def norm(sym):      # the anonymous-namespace tag hashes the build path: everything else (name, every template argument) must match
+        return re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+", "_ANON_", sym or "")
     for e in t.get("entries", []):
-        if e.get("kernel_mangled") == kernel_mangled and e.get("workload") == workload and e.get("real") == real:
+        if norm(e.get("kernel_mangled")) == norm(kernel_mangled) and e.get("workload") == workload and e.get("real") == real:
             return e.get("dram_bytes_per_launch"), e.get("source"), {k: e.get(k) for k in ("l1_data_pipe_pct_of_peak", "fp64_pipe_pct_of_peak", "dram_pct_of_peak",
                                                                                              "l1_hit_rate_pct", "l2_hit_rate_pct", "kernel_ms_under_ncu")}
     return None, "no ncu capture of this kernel instantiation on this workload (profiles/traffic.json holds others)", None
@@ -691,14 +695,21 @@ def main():
     r = run_gpu(args.workload, args, rank, world, local_rank, torch, dist, steps=args.steps, warmup=args.warmup,
                 do_e2e=not args.no_e2e, do_parity=not args.no_parity, do_moving=not args.no_moving)
     extras = {}
-    if world == 1 and not args.no_extra and args.workload == DEFAULT_WORKLOAD:
-        for wl, k in (("wcsph3d_10m", 20), ("dem3d_1m", 20), ("wcsph2d_20k", 50), ("coupled3d_2m", 10)):
+    if not args.no_extra and args.workload == DEFAULT_WORKLOAD:
+        # N = 1: the other BASELINE configs; every N: configs[4], the coupled SPH-DEM block of 20 M particles, cut into N slabs like the
+        # headline (its strong-scaling curve comes out of the same driver runs)
+        todo = [("wcsph3d_10m", 20), ("dem3d_1m", 20), ("wcsph2d_20k", 50), ("coupled3d_2m", 10)] if world == 1 else []
+        todo.append(("coupled3d_20m", 10))
+        for wl, k in todo:
             try:
                 x = run_gpu(wl, args, rank, world, local_rank, torch, dist, steps=k, warmup=3, do_e2e=False,
                             do_parity=wl == "wcsph3d_10m", do_moving=True)
-                extras[wl] = {kk: x[kk] for kk in ("value", "ms_per_step", "config", "run", "roofline", "gpu_launches", "parity_check", "moving")}
-                extras[wl]["steps"] = k
+                if rank == 0:
+                    extras[wl] = {kk: x[kk] for kk in ("value", "ms_per_step", "scaling", "config", "run", "roofline", "gpu_launches", "parity_check", "moving")}
+                    extras[wl]["steps"] = k
             except Exception as e:          # an extra must never take the headline down
+                if world > 1:
+                    raise                   # (with other ranks waiting in a collective there is nothing to salvage: fail loudly)
                 extras[wl] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
