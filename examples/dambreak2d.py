@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--dt", type=float, default=2e-5)
     ap.add_argument("--every", type=int, default=500, help="snapshot interval in steps")
     ap.add_argument("--wall-pressure", action="store_true", help="dummy-particle wall pressure (boundary_model = 1, DESIGN.md 4d)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of pst_step from the host instead of replaying a CUDA graph")
     ap.add_argument("--out", default="dambreak2d_out")
     args = ap.parse_args()
 
@@ -48,7 +49,10 @@ def main():
         pb.codegen.b200.run(ctx, fused)
         print(f"{block.n} particles ({int(fluid.sum())} fluid), {len(ctx.dump_pairs(0))} neighbour pairs, "
               f"max |a| = {np.abs(ctx.download('av')).max():.3g} m/s^2")
-        # ... then the stepping loop (re-sort -> EOS -> [wall pressure] -> fused pair kernel -> semi-implicit Euler)
+        # ... then the stepping loop (re-sort -> EOS -> [wall pressure] -> fused pair kernel -> semi-implicit Euler); at this size a
+        # step is launch-bound, so pst_step replays it as a CUDA graph (two steps per replay; bit-identical to eager launches)
+        if not args.no_graph:
+            ctx.set_option("graph", 1)
         t0 = time.perf_counter()
         for done in range(0, args.steps, args.every):
             k = min(args.every, args.steps - done)

@@ -117,3 +117,32 @@ def test_split_layers_and_bounds():
     assert sum(k for _, k in decomp.split_layers(83 * 8, 8)) == 83 * 8
     lo, hi = decomp.slab_bounds(0.0, 0.012, 83, 2)
     assert abs(lo - 2 * 83 * 0.012) < 1e-15 and abs(hi - 3 * 83 * 0.012) < 1e-15
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_bench_slabs_partition_the_block(world):
+    """bench.py cuts the SAME lattice block into `world` x-slabs of whole cell layers (strong scaling): every particle of the
+    block belongs to exactly one slab, slabs are contiguous in x and tile the box, and each rank generates its slab alone
+    (counter-based generator) with the values the whole block has."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from prestige_b200 import synth
+    nx, ny, nz = 57, 9, 11
+    whole = synth.wcsph_block_3d(nx, ny, nz, dx=bench.DX)
+    seen = np.zeros(whole.n, dtype=np.int64)
+    prev_hi = 0.0
+    for rank in range(world):
+        b, (lo_x, hi_x) = bench._slab_of(synth.wcsph_block_3d, nx, ny, nz, rank, world)
+        assert lo_x == pytest.approx(prev_hi)
+        prev_hi = hi_x
+        ids = b.meta["ids"].astype(np.int64)
+        seen[ids] += 1
+        for k in ("x", "u", "rho"):
+            assert np.array_equal(b.arrays[k], whole.arrays[k][ids])
+        inside = (b.arrays["x"] >= lo_x) | (rank == 0)
+        inside &= (b.arrays["x"] < hi_x) | (rank == world - 1)
+        assert inside.all()
+        cells = (hi_x - lo_x) / whole.cell_size
+        assert abs(cells - round(cells)) < 1e-9          # whole cell layers: what pst_comm_init requires
+    assert np.all(seen == 1)
+    assert prev_hi >= nx * bench.DX
