@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -128,3 +129,35 @@ def test_synth_configs():
     assert d.n == 1000 + 100 and d.max_contacts == 12
     s = d.shuffled()
     assert sorted(s.arrays["x"]) == sorted(d.arrays["x"])
+
+
+# ---- bench.py plumbing that needs no GPU -------------------------------------------------------
+def test_bench_traffic_lookup_matches_only_the_same_instantiation():
+    """roofline.traffic / ncu_units come from profiles/traffic.json and are attached only to the kernel instantiation that was
+    profiled: same mangled symbol (the anonymous-namespace tag, which hashes the build path, aside), same workload, same real."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import json
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    e = next(x for x in t["entries"] if "k_wcsph_zrun" in x["kernel_mangled"] and x["workload"] == "wcsph3d_10m")
+    sym = e["kernel_mangled"]
+    got, src, units = bench.traffic_for(sym, "wcsph3d_10m", "f64")
+    assert got == e["dram_bytes_per_launch"] and units["l1_data_pipe_pct_of_peak"] > 50
+    moved = re.sub(r"_GLOBAL__N__[0-9a-f]+_", "_GLOBAL__N__deadbeef_", sym)          # the same kernel built under another path
+    assert moved != sym and bench.traffic_for(moved, "wcsph3d_10m", "f64")[0] == got
+    other = sym.replace("ELb1ELb1ELb0ELb1ELb1E", "ELb1ELb1ELb0ELb0ELb1E")              # another instantiation (UNI off)
+    assert other != sym and bench.traffic_for(other, "wcsph3d_10m", "f64")[0] is None
+    assert bench.traffic_for(sym, "wcsph3d_10m", "f32")[0] is None
+    assert bench.traffic_for(sym, "dem3d_1m", "f64")[0] is None
+
+
+def test_bench_config_is_the_same_object_in_both_arms():
+    """The CPU arm (--impl reference) and the GPU arm describe the workload with the same `config` keys and values (the GPU arm's
+    run-specific details live under `run`), so the driver compares like with like."""
+    sys.path.insert(0, ROOT)
+    import bench
+    b = synth.wcsph_block_3d(6, 6, 6)
+    c1 = bench.workload_config("wcsph3d_80m", b, 1, "f64", "linear")
+    c8 = bench.workload_config("wcsph3d_80m", b, 8, "f64", "linear", n_total=b.n)
+    assert c1 == c8 and set(c1) == {"workload", "particles", "dim", "physics", "real", "key", "geometry", "timed", "l2"}
+    assert "BASELINE configs[3]" in c1["geometry"]
