@@ -455,6 +455,7 @@ static pst_status build_pass(pst_ctx* ctx, int mig_l, int mig_r) {
         auto in_fused = [&](const PstArray& a) {
             if (!fused || a.rows != 1) return false;
             for (const char* nm : {"x", "y", "z", "u", "v", "w", "rho", "m", "h"}) if (a.name == nm) return true;
+            if ((a.name == "tag" || a.name == "id") && a.esize == 4) return true;      // ride along in k_permute_eos
             return false;
         };
         for (int pass = 0; pass < 2; ++pass)

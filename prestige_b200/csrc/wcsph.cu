@@ -138,6 +138,8 @@ struct PermEosArgs {
     R* dst[9];
     R *p, *por2, *rec;
     PosF<R> F;
+    const uint32_t* src4[2];   // tag and id (4-byte rows; null if the context has none): they ride along, so a WCSPH context needs no
+    uint32_t* dst4[2];         // second, generic permute launch for two small arrays
 };
 template <class R>
 __global__ void __launch_bounds__(256) k_permute_eos(WcsphConst<R> C, int n, const uint32_t* __restrict__ perm, PermEosArgs<R> P) {
@@ -150,6 +152,9 @@ __global__ void __launch_bounds__(256) k_permute_eos(WcsphConst<R> C, int n, con
 #pragma unroll
     for (int a = 0; a < 9; ++a)
         if (P.dst[a]) P.dst[a][s] = v[a];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+        if (P.src4[a]) P.dst4[a][s] = __ldg(P.src4[a] + o);
     const R pr = tait_pressure<R>(C, v[6]);
     const R q = pr / (v[6] * v[6]);
     P.p[s] = pr;
@@ -1256,6 +1261,13 @@ static pst_status launch_permute_eos(pst_ctx* ctx, const uint32_t* perm, int n) 
     P.p = pst_ptr<R>(ctx, "p"); P.por2 = pst_ptr<R>(ctx, "por2");
     P.rec = rec_ptr<R>(ctx);
     P.F = pos_f<R>(ctx);
+    const char* names4[2] = {"tag", "id"};
+    for (int a = 0; a < 2; ++a) {
+        PstArray* arr = pst_find(ctx, names4[a]);
+        const bool ok = arr && arr->esize == 4 && arr->rows == 1 && (arr->flags & PST_ARRAY_PERSISTENT);
+        P.src4[a] = ok ? pst_ptr<uint32_t>(ctx, arr, 0, arr->cur) : nullptr;
+        P.dst4[a] = ok ? pst_ptr<uint32_t>(ctx, arr, 0, 1 - arr->cur) : nullptr;
+    }
     PST_LAUNCH(ctx, k_permute_eos<R>, blocks_for(n, 256), 256, 0, make_const<R>(ctx), n, perm, P);
     return PST_OK;
 }

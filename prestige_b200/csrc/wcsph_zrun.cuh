@@ -53,7 +53,7 @@ __global__ void k_set_int(int* p, int v) { *p = v; }
 // of its own and its staged runs (own columns + one column around, `sub` fine cells above and below) hold <= jcap candidates
 template <int DIM, int TA, int TB>
 __global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, int cx_lo, int cx_hi, int tiles_x, int tiles_y, int target, int gfcap,
-                                                    int sub, int jcap, const int32_t* __restrict__ cs, int4* __restrict__ tiles, int* __restrict__ off, int write) {
+                                                    int sub, int jcap, const int32_t* __restrict__ cs, int4* __restrict__ slots, int* __restrict__ off) {
     constexpr int BB = DIM == 3 ? TB : 1;
     constexpr int NRX = TA + 2, NRY = DIM == 3 ? BB + 2 : 1;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -89,12 +89,13 @@ __global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, in
     int c0 = C(0);
     const int cend = C(nf);
     const int pad = 3 * NRX * NRY;          // alignment slack of the staged runs
-    // Two passes of the same cut (write = 0: count into off[wid]; an exclusive scan; write = 1: fill from off[wid]), so the list
-    // is in (tx, ty, f0) order: the CTAs then walk the domain like a launch in that order would, and the candidates two
+    // ONE pass of the cut: the tiles of this column pair go to its own slot range (stride nf: a tile holds at least one fine cell)
+    // and their number to off[wid]; after an exclusive scan of the counts k_ztile_compact moves them to their final places, so the
+    // list is in (tx, ty, f0) order: the CTAs then walk the domain like a launch in that order would, and the candidates two
     // neighbouring tile columns share are still in L2 when the second one needs them (an unordered list reads every record
     // ~3x from DRAM: 2.8 GB instead of 0.9 GB at 10 M particles, profiles/r2_exp_log.txt)
     int nt = 0;
-    const int k0 = write ? off[wid] : 0;
+    int4* const mine = slots + (size_t)wid * nf;
     while (f0 < nf && c0 < cend) {          // (c0 == cend: nothing above f0)
         int best = f0 + 1;                  // at least one fine cell per tile (a cell denser than the target runs in several rounds)
         const int s0 = Sg(max(f0 - sub, 0));
@@ -109,12 +110,20 @@ __global__ void __launch_bounds__(128) k_ztile_list(int ncx, int ncy, int nf, in
         }
         const int cb = C(best);
         if (cb > c0) {
-            if (write && lane == 0) tiles[k0 + nt] = make_int4(tx, ty, f0, best - f0);
+            if (lane == 0) mine[nt] = make_int4(tx, ty, f0, best - f0);
             ++nt;
         }
         f0 = best; c0 = cb;
     }
-    if (!write && lane == 0) off[wid] = nt;
+    if (lane == 0) off[wid] = nt;
+}
+
+// one warp per column pair: its tiles from the slot range to their place in the ordered list (off = the scanned counts)
+__global__ void __launch_bounds__(128) k_ztile_compact(int npairs, int nf, const int4* __restrict__ slots, const int* __restrict__ off, int4* __restrict__ tiles) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= npairs) return;
+    const int b = off[wid], e = off[wid + 1];
+    for (int i = lane; i < e - b; i += 32) tiles[b + i] = slots[(size_t)wid * nf + i];
 }
 
 // ---- TMA (1-D bulk copy) + mbarrier, sm_90+ PTX: the staged rows of a tile are contiguous ranges of the f32 position arrays
@@ -594,7 +603,7 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     if (cap > ctx->ztiles_cap) {
         PST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->ztiles); ctx->ztiles = nullptr;
-        PST_CUDA(ctx, cudaMalloc(&ctx->ztiles, cap * sizeof(int4)));
+        PST_CUDA(ctx, cudaMalloc(&ctx->ztiles, 2 * cap * sizeof(int4)));      // the ordered list, then the per-pair slot ranges of the cut
         ctx->ztiles_cap = cap;
         ctx->ztiles_key = 0;
     }
@@ -609,12 +618,12 @@ pst_status launch_zrun_shape(pst_ctx* ctx, bool cont, bool mom) {
     int* const d_off = ctx->d_ztile_count + 1;
     const uint64_t key = ctx->build_epoch * 1000003ull + (uint64_t)gfcap * 4099 + (uint64_t)target + (uint64_t)T.jcap * 7919 + (uint64_t)NT * 104729;
     if (key != ctx->ztiles_key) {
+        int4* const slots = (int4*)ctx->ztiles + cap;
         PST_CUDA(ctx, cudaMemsetAsync(d_off + nwarps, 0, sizeof(int), ctx->stream));
-        for (int write = 0; write < 2; ++write) {
-            PST_LAUNCH(ctx, (k_ztile_list<DIM, TA, TB>), blocks_for((size_t)nwarps * 32, 128), 128, 0, g.n[0], DIM == 3 ? g.n[1] : 1, nf, g.cx_lo, g.cx_hi,
-                       tiles_x, tiles_y, target, gfcap, S, user_G > 0 ? 0x3fffffff : T.jcap, ctx->cell_start, (int4*)ctx->ztiles, d_off, write);
-            if (!write) PST_TRY(pst_scan_exclusive(ctx, d_off, nwarps + 1));     // off[nwarps] = number of tiles
-        }
+        PST_LAUNCH(ctx, (k_ztile_list<DIM, TA, TB>), blocks_for((size_t)nwarps * 32, 128), 128, 0, g.n[0], DIM == 3 ? g.n[1] : 1, nf, g.cx_lo, g.cx_hi,
+                   tiles_x, tiles_y, target, gfcap, S, user_G > 0 ? 0x3fffffff : T.jcap, ctx->cell_start, slots, d_off);
+        PST_TRY(pst_scan_exclusive(ctx, d_off, nwarps + 1));     // off[nwarps] = number of tiles
+        PST_LAUNCH(ctx, k_ztile_compact, blocks_for((size_t)nwarps * 32, 128), 128, 0, nwarps, nf, slots, d_off, (int4*)ctx->ztiles);
         ctx->ztiles_key = key;
     }
     // TMA staging works on f32 coordinates relative to the GRID origin: their error grows with the box, and so must the margin of
